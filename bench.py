@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- SafeOpt/GoOSE grid step on N B200s: expander pair-evals/s (+ step time).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c4|c5|c4s] [--mode fantasy|lipschitz] [--precision tf32|fp64]
+
+A "step" = model upload -> GP posterior over the grid for all G GPs -> safe/minimiser/unsafe sets ->
+Lipschitz constants (Lipschitz mode) -> expander pair kernel -> arg-reductions -> x_new.  It EXCLUDES the
+plant evaluation and the hyper-parameter fit, which stay on the host in the reference too.
+Workload at N=1: BASELINE.json configs[3] "synthetic SafeOpt expander step: 2^20-point d=4 grid, n=512
+observations, 3 constraint GPs" (C4); the grid is sharded over the ranks (strong scaling, fixed N).
+`value` = pair-evals of the whole job / device time of the step (CUDA events on the launch stream, max
+over ranks); `e2e` = the same through GridEngine.safeopt_step with HOST buffers (model H2D, result and
+safe-mask D2H inside the timed region, wall clock around a device sync).
+--impl reference times the NumPy oracle (the port of the reference's arithmetic; JAX is not installed)
+on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--mode", default=os.environ.get("SBO_BENCH_MODE", "lipschitz"))
+    ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "fp64"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peaks", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name):
+    import sbo_b200  # noqa: F401
+    from sbo_b200 import workloads
+    if name == "c4":
+        return workloads.c4(), "C4: synthetic SafeOpt expander step, d=4, N=32^4=2^20 grid, n=512, G=4 (3 constraints)"
+    if name == "c5":
+        return workloads.c5(), "C5: synthetic step, d=6, N=16^6=2^24 grid, n=2048, G=4 (3 constraints)"
+    if name == "c4s":
+        return workloads.c4(pts_per_dim=16, n=128), "C4-small: d=4, N=16^4, n=128, G=4 (debug size)"
+    raise SystemExit(f"unknown workload {name}")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for nm, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy port of the reference's arithmetic) on a bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_sample_step(ds, lo, hi, pts, beta, mode, n_points=4096, n_x=512, n_z=4096, seed=0):
+    """One bounded CPU 'step': posterior (reference inverse form) at n_points random grid points, sets, then
+    the pair test for n_x safe x n_z unsafe sampled points.  Returns per-unit costs for extrapolation."""
+    from oracle import gp_oracle as O
+    G = ds["Y_norm"].shape[1]
+    d = len(pts)
+    rng = np.random.default_rng(seed)
+    axes = O.grid_axes(lo, hi, pts)
+    idx = rng.integers(0, pts[0], size=(n_points, d))
+    P = np.column_stack([axes[k][idx[:, k]] for k in range(d)])
+    dso = dict(ds)
+    t0 = time.perf_counter()
+    dso["invKopt"] = [np.linalg.inv(O.build_K(ds["X_norm"], ds["hypopt"][:, i])) for i in range(G)]   # GP_Safe.py:232
+    t_model = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mean, var = O.posterior_inv(P, dso)
+    lcb, ucb = O.bounds(mean, var, beta)
+    S, Z = O.safe_mask(lcb), O.unsafe_mask(lcb)
+    t_post = time.perf_counter() - t0
+    xs, zs = np.flatnonzero(S)[:n_x], np.flatnonzero(Z)[:n_z]
+    t0 = time.perf_counter()
+    if xs.size and zs.size:
+        Ssub = np.zeros(n_points, bool); Ssub[xs] = True
+        Zsub = np.zeros(n_points, bool); Zsub[zs] = True
+        if mode == "fantasy":
+            O.fantasy_counts(P, dso, beta, Ssub, Zsub, dtype=np.float32)
+        else:
+            L = [1.0] * G
+            O.expander_lipschitz(P, Ssub, Zsub, ucb, var, L)
+    t_pairs = time.perf_counter() - t0
+    pairs = int(xs.size) * int(zs.size) * (G - 1)
+    return {"t_model": t_model, "t_post": t_post, "n_points": n_points, "t_pairs": t_pairs, "pairs": pairs,
+            "safe_frac": float(S.mean()), "unsafe_frac": float(Z.mean())}
+
+
+def cpu_extrapolate(s, N, pairs_full):
+    """Linear extrapolation of a sampled CPU step to the full workload (labelled as such)."""
+    t_full = s["t_model"] + s["t_post"] * (N / s["n_points"]) + (s["t_pairs"] * (pairs_full / s["pairs"]) if s["pairs"] else 0.0)
+    return t_full
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    (ds, lo, hi, pts, beta), wl_name = workload(args.workload)
+    N = int(np.prod(pts))
+    G = ds["Y_norm"].shape[1]
+    cores = os.cpu_count()
+    times, samples = [], []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        s = cpu_sample_step(ds, lo, hi, pts, beta, args.mode, seed=it)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt); samples.append(s)
+    s = samples[-1]
+    # full-workload pair count estimated from the sample's safe/unsafe fractions
+    sf = float(np.mean([x["safe_frac"] for x in samples])); uf = float(np.mean([x["unsafe_frac"] for x in samples]))
+    pairs_full = sf * N * uf * N * (G - 1)
+    t_full = float(np.mean([cpu_extrapolate(x, N, pairs_full) for x in samples]))
+    value = pairs_full / t_full
+    sample_desc = (f"{s['n_points']} random grid points for the posterior+sets, {s['pairs']} pair-evals "
+                   f"({args.mode} mode); step time extrapolated linearly to N={N} points and {pairs_full:.3g} pairs")
+    line = {"impl": "reference", "metric": "expander_pair_evals_per_s", "value": value, "unit": "pair-evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "mode": args.mode, "note": "NumPy restatement of the reference, not JAX"},
+            "cpu_baseline": {"value": value, "unit": "pair-evals/s", "cores": cores, "kind": "port", "sample": sample_desc},
+            "e2e": {"value": value, "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "sample_ms_per_step": float(np.mean(times)) * 1e3}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def measure_peaks(torch, dev):
+    """Yard-sticks for the roofline denominators MEASURED_PEAKS.json lacks: cuBLAS FP64 and TF32 GEMM."""
+    out = {}
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        for name, dt, n in (("fp64_tflops", torch.float64, 4096), ("tf32_tflops", torch.float32, 8192)):
+            a = torch.randn(n, n, device=dev, dtype=dt); b = torch.randn(n, n, device=dev, dtype=dt)
+            for _ in range(2):
+                torch.matmul(a, b)
+            best = 1e9
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+            del a, b
+    except Exception as e:  # pragma: no cover
+        out["error"] = str(e)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sbo_b200
+    from sbo_b200 import _capi as capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    (ds, lo, hi, pts, beta), wl_name = workload(args.workload)
+    N = int(np.prod(pts))
+    G = ds["Y_norm"].shape[1]
+    n, d = ds["X_norm"].shape
+    stream = torch.cuda.Stream(device=dev)
+    eng = sbo_b200.GridEngine(local, stream=stream.cuda_stream)
+    eng.set_grid(lo, hi, pts)
+    per = (N + world - 1) // world
+    first = rank * per
+    count = min(per, N - first)
+    if world > 1:
+        eng.set_shard(first, count)
+    prec = capi.PREC_TF32 if args.precision == "tf32" else capi.PREC_FP64
+    fantasy = args.mode == "fantasy"
+
+    def step(upload=True):
+        """One acquisition step on this rank's shard.  Multi-GPU: scalar all-reduces between the stages."""
+        if world == 1:
+            return eng.safeopt_step(ds, beta, mode=args.mode, precision=args.precision, upload=upload)
+        from sbo_b200 import sharded
+        return sharded.safeopt_step(eng, ds, beta, mode=args.mode, precision=args.precision, upload=upload)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed steps (value) ----
+    for _ in range(args.warmup):
+        step()
+    eng.kernel_launches(reset=True)
+    clocks = Clocks(local)
+    barrier()
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    phases = []
+    res = None
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ev[k][0].record(stream)
+            res = step()
+            ev[k][1].record(stream)
+        phases.append(eng.phase_ms())
+    barrier()
+    clk = clocks.stop()
+    launches = eng.kernel_launches()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # ---- end-to-end steps (host buffers in, host results out) ----
+    t_e2e = []
+    for k in range(max(2, args.steps)):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        r2 = step(upload=True)
+        safe = eng.mask(capi.MASK_SAFE)
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(t_e2e[1:])) if len(t_e2e) > 1 else t_e2e[0]
+    h2d = int(sum(np.asarray(ds[k]).nbytes for k in ("X_norm", "Y_norm", "X_mean", "X_std", "Y_mean", "Y_std", "hypopt")))
+    d2h = int(safe.size // 8 + 512)
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    ex = res["expander"]
+    pairs = int(ex["pairs_algorithmic"])
+    if world > 1:
+        t = torch.tensor([pairs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pairs = int(t[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+    peaks = {} if args.no_peaks else measure_peaks(torch, dev)
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # ---- roofline of the dominant kernel ----
+    npad = ((n + 63) // 64) * 64
+    if fantasy:
+        flops = pairs * (2.0 * npad + 3 * d + 20)          # pairs*(G-1) counted in `pairs`
+        t_k = ph["pairs"] * 1e-3
+        peak = peaks.get("tf32_tflops" if args.precision == "tf32" else "fp64_tflops")
+        roof = {"kernel": "fantasy expander GEMM", "bound": "tensor", "achieved": flops / t_k / 1e12 if t_k > 0 else None,
+                "peak": peak, "unit": "TFLOP/s", "traffic": None,
+                "peak_source": "cuBLAS %s GEMM measured in this run" % ("TF32" if args.precision == "tf32" else "FP64")}
+    else:
+        flops = float(G) * N / world * (float(n) * n + n * (3 * d + 6))     # SURVEY 8d F_post (per rank)
+        t_k = (ph["solve"] + ph["crosscov"]) * 1e-3
+        roof = {"kernel": "posterior solve (k_solve_var) + cross-covariance", "bound": "tensor",
+                "achieved": flops / t_k / 1e12 if t_k > 0 else None, "peak": peaks.get("fp64_tflops"), "unit": "TFLOP/s",
+                "traffic": None, "peak_source": "cuBLAS FP64 GEMM measured in this run (FP64 has no tcgen05 path)"}
+    roof["frac"] = (roof["achieved"] / roof["peak"]) if roof.get("achieved") and roof.get("peak") else None
+    value = pairs / (ms * 1e-3)
+    line = {"metric": "expander_pair_evals_per_s", "value": value, "unit": "pair-evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "tf32" if (fantasy and args.precision == "tf32") else "f64",
+            "data": "synthetic",
+            "config": {"workload": wl_name, "mode": args.mode, "precision": args.precision, "N": N, "n": n, "d": d, "G": G,
+                       "beta": beta, "n_safe": int(res["n_safe"]), "n_unsafe": int(res["n_unsafe"]), "n_min": int(res["n_min"]),
+                       "pairs": pairs, "pairs_evaluated": int(ex["pairs_evaluated"]), "x_new_idx": int(res["x_new_idx"]),
+                       "l2": "256 MiB flush buffer written between timed steps; working set >> L2",
+                       "excludes": "plant evaluation and hyper-parameter fit (host side in the reference too)"},
+            "phase_ms": ph, "clocks": clk, "gpu_launches": int(launches // max(1, args.steps)),
+            "e2e": {"value": pairs / e2e_s, "unit": "pair-evals/s", "ms_per_step": e2e_s * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roof, "peaks": {**peaks, "hbm_gbs": mp.get("hbm_gbs"), "bf16_tflops": mp.get("bf16_tflops")}}
+    if not args.no_cpu_baseline and world == 1:
+        s = cpu_sample_step(ds, lo, hi, pts, beta, args.mode)
+        t_full = cpu_extrapolate(s, N, pairs)
+        line["cpu_baseline"] = {"value": pairs / t_full, "unit": "pair-evals/s", "cores": os.cpu_count(), "kind": "port",
+                                "ms_per_step_extrapolated": t_full * 1e3,
+                                "sample": f"{s['n_points']} random grid points (posterior+sets) and {s['pairs']} pair-evals "
+                                          f"timed on the host, extrapolated linearly to the full step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,167 @@
+/* sbo_b200.h -- C ABI of the B200-native SafeOpt/GoOSE grid hot path.
+ *
+ * Drop-in boundary for the ONE data-parallel path of dleeim/Safe-Bayesian-Optimization:
+ * per acquisition step, GP posteriors over a dense candidate grid, then the safe set,
+ * minimiser set, expander set / GoOSE target and the arg-reductions that pick x_new.
+ * The reference has no native code and no FFI; each entry point below cites the
+ * reference *Python* interface it replaces (paths relative to the reference root).
+ * Python binds this library with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative sbo_status otherwise; the message
+ *     is available from sbo_last_error().  Nothing aborts.  There is NO CPU fallback: a
+ *     context cannot be created without a CUDA device.
+ *   - host pointers unless the name ends in _dev.  The caller owns all in/out buffers;
+ *     the context owns device copies, workspaces and (unless sbo_set_stream) its stream.
+ *   - calls are synchronous w.r.t. returned host data; one host thread per context.
+ *   - all floating-point data is FP64 (the reference runs jax_enable_x64, GP_Safe.py:8).
+ *   - grid points are numbered with x_0 the fastest axis (test/test_SafeOpt.py:324-334:
+ *     meshgrid 'xy' + ravel  =>  p = r*400 + c).  Indices returned are GLOBAL grid
+ *     indices (int64); -1 means "empty set".
+ *   - per-point arrays are GP-major: mean[i*count + p], i = GP index (0 = objective).
+ *   - bitmasks are little-endian uint32 words over the LOCAL shard: bit (p&31) of word p>>5.
+ */
+#ifndef SBO_B200_H
+#define SBO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBO_MAX_D 8   /* input dimensions  */
+#define SBO_MAX_G 8   /* GPs: 1 objective + up to 7 constraints */
+
+typedef struct sbo_ctx sbo_ctx;
+
+enum sbo_status {
+  SBO_OK = 0,
+  SBO_ERR_INVALID = -1,   /* bad argument / call order  */
+  SBO_ERR_CUDA = -2,      /* CUDA runtime error         */
+  SBO_ERR_NUMERIC = -3,   /* K not positive definite    */
+  SBO_ERR_NOMEM = -4
+};
+
+/* unsafe-set rule.  ALL: Z = {z : lcb_i(z) <= 0 for every constraint}  -- what the reference's
+ * lcb_constraint_min (returns the MAX, models/SafeOpt.py:73-77) + "<= 0" (SafeOpt.py:109) encodes.
+ * ANY: Z = {z : some lcb_i(z) < 0} = complement of S. */
+enum sbo_unsafe_rule { SBO_UNSAFE_ALL = 0, SBO_UNSAFE_ANY = 1 };
+
+enum sbo_expander_mode { SBO_MODE_LIPSCHITZ = 0, SBO_MODE_FANTASY = 1 };
+enum sbo_precision { SBO_PREC_FP64 = 0, SBO_PREC_TF32 = 1 };
+
+/* score selectors for sbo_argreduce */
+enum sbo_reduce_kind {
+  SBO_ARGMAX_VAR0 = 0,     /* max objective variance over a mask        (SafeOpt.py:55,65,92) */
+  SBO_ARGMIN_LCB0 = 1,     /* min lcb_0 over a mask                     (GoOSE.py:63-67,110)  */
+  SBO_ARGMIN_UCB0 = 2,     /* min ucb_0 over a mask                     (SafeOpt.py:47-51)    */
+  SBO_ARGMIN_DIST = 3      /* min ||x - target||_2 over a mask          (GoOSE.py:116-119)    */
+};
+enum sbo_mask_kind { SBO_MASK_SAFE = 0, SBO_MASK_MIN = 1, SBO_MASK_UNSAFE = 2, SBO_MASK_USER = 3 };
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int sbo_create(int device, sbo_ctx** out);
+int sbo_destroy(sbo_ctx* ctx);
+const char* sbo_last_error(const sbo_ctx* ctx);        /* ctx may be NULL: last create() error */
+int sbo_set_stream(sbo_ctx* ctx, void* cuda_stream);   /* run on the caller's stream (e.g. torch's) */
+int sbo_version(void);
+
+/* ---- model upload:  GP.inference_datasets  (models/GP_Safe.py:16-23,236-245) ------------
+ * X_norm[n*d] row-major, Y_norm[n*G] row-major, hyp[(d+2)*G] row-major with rows
+ * [0:d] = 1/2 log ell, [d] = 1/2 log sf2, [d+1] = 1/2 log sn2  (GP_Safe.py:226-229).
+ * Builds K_i = sf2*exp(-1/2 dist) + (sn2 + eps_f32) I  (GP_Safe.py:229-231) on the device,
+ * factorises it (K = L L^T), forms W = L^-1 and alpha = K^-1 (Y_i - m0_i) with the
+ * reference's prior mean m0 = -2*Y_mean/Y_std, m0[0] = 0  (GP_Safe.py:331-332).
+ * Replaces jnp.linalg.inv(Kopt) (GP_Safe.py:232): the explicit inverse is never needed. */
+int sbo_set_model(sbo_ctx* ctx, int n, int d, int G,
+                  const double* X_norm, const double* Y_norm,
+                  const double* X_mean, const double* X_std,
+                  const double* Y_mean, const double* Y_std,
+                  const double* hyp);
+/* debug / test read-back (any pointer may be NULL): K,L,W are [G][n][n] row-major, alpha [G][n] */
+int sbo_get_model(sbo_ctx* ctx, double* L, double* W, double* alpha);
+
+/* ---- candidate points:  create_data_for_plot()  (test/test_SafeOpt.py:324-334) ---------
+ * sbo_set_grid: implicit meshgrid of per-axis numpy.linspace(lo_k, hi_k, pts_k), x_0 fastest.
+ * sbo_set_points: explicit N x d row-major points.
+ * sbo_set_shard: this context (rank) owns global points [first, first+count); default = all. */
+int sbo_set_grid(sbo_ctx* ctx, int d, const int64_t* pts_per_dim, const double* lo, const double* hi);
+int sbo_set_points(sbo_ctx* ctx, int64_t N, int d, const double* pts);
+int sbo_set_shard(sbo_ctx* ctx, int64_t first, int64_t count);
+int sbo_point_coords(sbo_ctx* ctx, int64_t global_idx, double* x /* d */);
+
+/* ---- posterior:  GP.GP_inference vmapped over the grid  (GP_Safe.py:310-352) -------------
+ * mean/var: [G*count] GP-major, raw (un-normalised) units, var clamped >= 0; NULL = keep on device.
+ * with_grad != 0 also accumulates L_i = max_p ||grad mu_i(p)||_inf  (SafeOpt.py:68-83).
+ * keep_v != 0 keeps V_i = L_i^-1 K_i(X, .) for the fantasy expander (constraints only):
+ *   1 = FP64 rows, 2 = FP32 rows (TF32 operand). */
+int sbo_posterior(sbo_ctx* ctx, int with_grad, int keep_v, double* mean, double* var);
+/* GP_inference at m arbitrary points (the single-point API behind BO.mean/ucb/lcb,
+ * SafeOpt.py:29-45): x[m*d] row-major -> mean[m*G], var[m*G] POINT-major like the reference. */
+int sbo_point_posterior(sbo_ctx* ctx, int64_t m, const double* x, double* mean, double* var);
+/* max_p ||grad mu_i||_inf over the local shard, i = 0..G-1 (valid after sbo_posterior(with_grad=1)) */
+int sbo_lipschitz(sbo_ctx* ctx, double* L /* G */);
+/* d mu_i / d x at m arbitrary points: grad[m*d]  (BO.infnorm_mean_grad's autodiff, SafeOpt.py:68-71) */
+int sbo_point_mean_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad);
+
+/* ---- sets:  SafeOpt.py:47-66, GoOSE.py:22-31,63-67 -----------------------------------------
+ * pass 1: lcb/ucb, S = {lcb_i >= 0 (or > 0 if strict) for all i>=1}, Z by rule,
+ *         min_S ucb_0 and argmin_S lcb_0.
+ * pass 2: M = {x in S : lcb_0(x) <= min_ucb0} and argmax_M var_0   (SafeOpt.Minimizer).
+ * Multi-GPU: all-reduce-min min_ucb0 between the passes and hand the global value to pass 2. */
+typedef struct sbo_sets_result {
+  int64_t n_safe, n_unsafe, n_min;
+  double  min_ucb0;      int64_t min_ucb0_idx;     /* BO.minimize_obj_ucb   */
+  double  min_lcb0;      int64_t min_lcb0_idx;     /* BO.minimize_obj_lcb   */
+  double  minimizer_var; int64_t minimizer_idx;    /* BO.Minimizer: std = sqrt(var) */
+} sbo_sets_result;
+int sbo_sets_pass1(sbo_ctx* ctx, double beta, int unsafe_rule, int strict, sbo_sets_result* out);
+int sbo_sets_pass2(sbo_ctx* ctx, double min_ucb0, sbo_sets_result* out);
+int sbo_sets(sbo_ctx* ctx, double beta, int unsafe_rule, int strict, sbo_sets_result* out);
+/* copy a bitmask of the local shard to the host: words[(count+31)/32] */
+int sbo_get_mask(sbo_ctx* ctx, int mask_kind, int which, uint32_t* words);
+int sbo_set_user_mask(sbo_ctx* ctx, const uint32_t* words);
+/* device addresses for collectives on the caller's side (NCCL via torch.distributed) */
+int sbo_mask_dev(sbo_ctx* ctx, int mask_kind, int which, void** dev_ptr, int64_t* n_words);
+int sbo_posterior_dev(sbo_ctx* ctx, void** mean_dev, void** var_dev);
+
+/* ---- arg-reductions (deterministic, lowest-index tie-break): SafeOpt.py:65,112; GoOSE.py:65,102,118 */
+int sbo_argreduce(sbo_ctx* ctx, int reduce_kind, int mask_kind, int which, const double* target /* d or NULL */,
+                  int64_t* idx, double* value);
+
+/* ---- expander / target pair kernels ----------------------------------------------------------
+ * Lipschitz mode (reference-exact): pair test  ucb_idx(x) - L_idx*||x - z + 1e-8||_2 >= 0 with
+ *   x in S, z in Z  (SafeOpt.py:85-88,109-111; GoOSE.py:69-72,99-101).  L[G]: entry idx is used for
+ *   constraint idx (the reference passes L_{G-1} for every idx, SafeOpt.py:110).
+ * Fantasy mode (north_star, not in the reference): rank-1 posterior update of every constraint GP with
+ *   the observation ucb_i(x); z is newly safe if every updated lcb_i(z) >= 0; g(x) = #newly-safe z.
+ *   precision: FP64 (SIMT reference kernel) or TF32 (tcgen05/TMEM GEMM, FP32 accumulate).
+ */
+typedef struct sbo_pair_result {
+  int64_t best_idx;  double best_value;          /* SafeOpt: argmax var_0 (value = var_0); GoOSE: argmin lcb_0 */
+  int64_t per_idx[SBO_MAX_G]; double per_value[SBO_MAX_G];   /* entry idx-1 for constraint idx */
+  int64_t n_x, n_z;                              /* candidate / unsafe points paired  */
+  int64_t pairs_algorithmic;                     /* n_x * n_z * (constraints)         */
+  int64_t pairs_evaluated;                       /* after tile-level early exit       */
+  int64_t n_hit;                                 /* |expander set| (union over idx) or |target set| */
+} sbo_pair_result;
+int sbo_expander(sbo_ctx* ctx, int mode, int precision, double beta, const double* L /* G, lipschitz mode */,
+                 sbo_pair_result* out, int32_t* counts /* count, fantasy mode, or NULL */);
+int sbo_goose_target(sbo_ctx* ctx, double beta, const double* L /* G */, sbo_pair_result* out);
+/* which = idx-1 (lipschitz/target: one mask per constraint) ; fantasy: which = 0 */
+#define SBO_MASK_EXPANDER 4
+#define SBO_MASK_TARGET   5
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* number of kernels this library launched on ctx since the last reset */
+int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
+/* device time of named phases of the last calls, milliseconds (CUDA events on the ctx stream).
+ * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce */
+int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
+int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBO_B200_H */

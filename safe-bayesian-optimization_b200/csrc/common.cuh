@@ -1,0 +1,178 @@
+// common.cuh -- context, device parameter blocks and helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/sbo_b200.h"
+
+#define SBO_EPS_F32 1.1920928955078125e-07   /* jnp.finfo(jnp.float32).eps, GP_Safe.py:229 */
+#define SBO_PAIR_OFFSET 1e-8                 /* SafeOpt.py:87 "+1e-8" */
+
+// ---------------------------------------------------------------------------------------------
+// device-visible parameter blocks (passed by value)
+// ---------------------------------------------------------------------------------------------
+struct GridSpec {
+  int kind;                 // 1 = implicit meshgrid, 2 = explicit points
+  int d;
+  long long N;              // global number of points
+  long long first, count;   // local shard
+  long long pts[SBO_MAX_D];
+  long long stride[SBO_MAX_D];
+  double lo[SBO_MAX_D], hi[SBO_MAX_D], step[SBO_MAX_D];
+  const double* explicit_pts;   // [N][d] row-major (global)
+};
+
+struct ModelSpec {
+  int n, npad, d, G;
+  const double* Xn;         // [npad][d], rows >= n are zero
+  const double* alpha;      // [G][npad]
+  const double* W;          // [G][npad][npad]  lower-triangular L^-1, zero elsewhere
+  double Xmean[SBO_MAX_D], Xstd[SBO_MAX_D];
+  double Ymean[SBO_MAX_G], Ystd[SBO_MAX_G], m0[SBO_MAX_G];
+  double inv_ell[SBO_MAX_G][SBO_MAX_D];
+  double sf2[SBO_MAX_G], sn2[SBO_MAX_G];   // sn2 already includes + eps_f32 (GP_Safe.py:229)
+};
+
+// numpy.linspace coordinate of axis k at index i: lo + i*step (two roundings, no FMA), last = hi.
+__device__ __forceinline__ double axis_coord(const GridSpec& g, int k, long long i) {
+  if (g.pts[k] > 1 && i == g.pts[k] - 1) return g.hi[k];
+  return __dadd_rn(__dmul_rn((double)i, g.step[k]), g.lo[k]);
+}
+// raw coordinates of GLOBAL point p
+__device__ __forceinline__ void point_coords(const GridSpec& g, long long p, double* x) {
+  if (g.kind == 1) {
+#pragma unroll
+    for (int k = 0; k < SBO_MAX_D; ++k)
+      if (k < g.d) x[k] = axis_coord(g, k, (p / g.stride[k]) % g.pts[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SBO_MAX_D; ++k)
+      if (k < g.d) x[k] = g.explicit_pts[p * g.d + k];
+  }
+}
+
+// confidence bounds, rounded like NumPy's  mean -/+ (b*sqrt(var))  (no FMA contraction)   SafeOpt.py:34-45
+__device__ __forceinline__ double lcb_of(double mean, double var, double beta) {
+  return __dsub_rn(mean, __dmul_rn(beta, sqrt(var)));
+}
+__device__ __forceinline__ double ucb_of(double mean, double var, double beta) {
+  return __dadd_rn(mean, __dmul_rn(beta, sqrt(var)));
+}
+
+// (value, index) pairs with lowest-index tie-break
+struct ArgVal { double v; long long i; };
+__device__ __forceinline__ ArgVal argmin2(ArgVal a, ArgVal b) {
+  return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgVal argmax2(ArgVal a, ArgVal b) {
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgVal shfl_xor_argval(ArgVal a, int m) {
+  ArgVal r;
+  r.v = __shfl_xor_sync(0xffffffffu, a.v, m);
+  r.i = __shfl_xor_sync(0xffffffffu, a.i, m);
+  return r;
+}
+#define SBO_IDX_NONE 0x7fffffffffffffffLL
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct sbo_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  int64_t launches = 0;
+
+  // model
+  bool have_model = false;
+  ModelSpec ms{};
+  DevBuf Xn, Yn, alpha, W, Kmat, info;
+  // grid
+  bool have_grid = false;
+  GridSpec gs{};
+  DevBuf pts;
+  // posterior (local shard)
+  bool have_post = false;
+  DevBuf mean, var, kx, lmax;
+  int keep_v = 0;            // 0 none, 1 fp64, 2 fp32
+  DevBuf vall;               // [(G-1)][count][npad] rows of V for the constraints
+  // sets
+  bool have_sets = false, have_sets2 = false;
+  double beta = 0.0;
+  DevBuf m_safe, m_unsafe, m_min, m_user, m_exp, m_tgt;
+  DevBuf partials, result;
+  // compaction / pair workspaces
+  DevBuf scan_a, scan_b, xs_idx, zs_idx, xs_pay, zs_pay, hits, counts, pairctr;
+  DevBuf imp_rows;
+  DevBuf vx, vz, aux_x, aux_z;
+  DevBuf pp_x, pp_m, pp_v, pp_k, pp_g;   // scratch of the arbitrary-point posterior calls
+  // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
+  struct EvPair { cudaEvent_t a, b; int phase; };
+  std::vector<EvPair> evlog;
+  std::vector<cudaEvent_t> evpool;
+  double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // options
+  int64_t opt_posterior_variant = 0;
+  int64_t opt_fantasy_variant = 0;
+};
+
+extern thread_local std::string g_sbo_last_error;
+
+int sbo_fail(sbo_ctx* ctx, int code, const std::string& msg);
+int sbo_ensure(sbo_ctx* ctx, DevBuf& b, size_t bytes);
+
+#define SBO_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return sbo_fail(ctx, SBO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+#define SBO_TRY(call)            \
+  do {                           \
+    int r__ = (call);            \
+    if (r__ != SBO_OK) return r__; \
+  } while (0)
+#define SBO_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return sbo_fail(ctx, SBO_ERR_INVALID, msg); \
+  } while (0)
+#define SBO_LAUNCH_CHECK()                                                                      \
+  do {                                                                                          \
+    ctx->launches++;                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return sbo_fail(ctx, SBO_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__) + \
+                                             " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+// phase ids: 0 model, 1 posterior cross-covariance, 2 posterior solve, 3 sets, 4 pairs, 5 arg-reduce, 6 pair prep
+void ev_begin(sbo_ctx* ctx, int phase);   // record a start event on the ctx stream
+void ev_end(sbo_ctx* ctx);                // record the matching stop event
+void ev_reset(sbo_ctx* ctx, int phase);   // zero a phase accumulator
+void ev_collect(sbo_ctx* ctx);            // (after a stream sync) add all logged pairs to phase_ms
+
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// implemented across the .cu files
+int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const double* Y_norm,
+                 const double* X_mean, const double* X_std, const double* Y_mean, const double* Y_std,
+                 const double* hyp);
+int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v);
+int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, double* var);
+int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad);
+int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result* out);
+int sets_pass2(sbo_ctx* ctx, double min_ucb0, sbo_sets_result* out);
+int argreduce_run(sbo_ctx* ctx, int kind, const uint32_t* mask_dev, const double* target_host, int64_t* idx, double* value);
+int compact_mask(sbo_ctx* ctx, const uint32_t* mask_dev, long long count, DevBuf& out_idx, long long* n_out);
+int pairs_lipschitz(sbo_ctx* ctx, bool goose, double beta, const double* L, sbo_pair_result* out);
+int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host);
+uint32_t* mask_ptr(sbo_ctx* ctx, int mask_kind, int which);
+long long mask_words(const sbo_ctx* ctx);

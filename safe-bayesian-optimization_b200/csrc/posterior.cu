@@ -1,0 +1,340 @@
+// posterior.cu -- GP posterior over the candidate grid (models/GP_Safe.py:310-352 vmapped, as in
+// test/test_SafeOpt.py:324-338), trsm form:
+//   k_j   = sf2 * exp(-1/2 sum_k (Xn_jk - xn_k)^2 / ell_k)                 (K1a, fused SE-ARD cross-covariance)
+//   mean  = (m0 + k . alpha) * Ystd + Ymean                                 (K1a epilogue)
+//   grad  = d mean / d x (analytic), L_i = max_p ||grad||_inf               (K1c, optional)
+//   v     = W k  (W = L^-1 lower triangular),  var = max(0, sf2 - |v|^2) * Ystd^2   (K1b)
+//   V rows are optionally kept (FP64 or TF32-rounded FP32) for the fantasy expander GEMM.
+#include "common.cuh"
+#include <math.h>
+
+#define XC_THREADS 128
+#define XC_JT 128
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a: cross-covariance tile -> Kx scratch [G][npad][P] (points contiguous), mean, optional gradient
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(XC_THREADS)
+k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __restrict__ Kx,
+           double* __restrict__ mean_out, long long out_ld, double* __restrict__ gradmax,
+           double* __restrict__ grad_out, int grad_gp) {
+  __shared__ double Xs[XC_JT * D];
+  __shared__ double As[XC_JT];
+  __shared__ double red[XC_THREADS / 32];
+  const int g = blockIdx.y;
+  const int pl = blockIdx.x * XC_THREADS + threadIdx.x;
+  const bool in_chunk = pl < P;
+  const bool ok = pl < valid;
+  double xn[D];
+  if (ok) {
+    double x[SBO_MAX_D];
+    point_coords(gs, gs.first + p0 + pl, x);
+#pragma unroll
+    for (int k = 0; k < D; ++k) xn[k] = (x[k] - ms.Xmean[k]) / ms.Xstd[k];       // GP_Safe.py:326
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) xn[k] = 0.0;
+  }
+  double iell[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) iell[k] = ms.inv_ell[g][k];
+  const double sf2 = ms.sf2[g];
+  const bool want_grad = (gradmax != nullptr) || (grad_out != nullptr && g == grad_gp);
+  double acc = 0.0;
+  double gk[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) gk[k] = 0.0;
+  double* kcol = Kx + (size_t)g * ms.npad * P + pl;
+  for (int j0 = 0; j0 < ms.npad; j0 += XC_JT) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < XC_JT * D; e += XC_THREADS)
+      Xs[e] = (j0 * D + e < ms.npad * D) ? ms.Xn[(size_t)j0 * D + e] : 0.0;
+    for (int e = threadIdx.x; e < XC_JT; e += XC_THREADS)
+      As[e] = (j0 + e < ms.npad) ? ms.alpha[(size_t)g * ms.npad + j0 + e] : 0.0;
+    __syncthreads();
+    const int jn = min(XC_JT, ms.npad - j0);
+    if (in_chunk) {
+      for (int j = 0; j < jn; ++j) {
+        double kv = 0.0;
+        if (ok && (j0 + j) < ms.n) {
+          double s = 0.0;
+          double df[D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) { df[k] = xn[k] - Xs[j * D + k]; s += df[k] * df[k] * iell[k]; }
+          kv = sf2 * exp(-0.5 * s);                                              // GP_Safe.py:165-166
+          const double w = As[j] * kv;
+          acc += w;
+          if (want_grad) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) gk[k] += w * df[k];
+          }
+        }
+        kcol[(size_t)(j0 + j) * P] = kv;
+      }
+    }
+  }
+  if (ok && mean_out) mean_out[(size_t)g * out_ld + p0 + pl] = (ms.m0[g] + acc) * ms.Ystd[g] + ms.Ymean[g];   // :342,346
+  if (want_grad) {
+    double gm = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const double gv = -gk[k] * iell[k] * ms.Ystd[g] / ms.Xstd[k];
+      if (ok && grad_out && g == grad_gp) grad_out[(size_t)(p0 + pl) * D + k] = gv;
+      gm = fmax(gm, fabs(gv));
+    }
+    if (gradmax) {
+      if (!ok) gm = 0.0;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, m));
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gm;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < XC_THREADS / 32; ++w) gm = fmax(gm, red[w]);
+        atomicMax((unsigned long long*)(gradmax + g), (unsigned long long)__double_as_longlong(gm));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b (variant 0, FP64 SIMT): V = W * Kx by 64x64x16 register tiles, triangular in K; the CTA owns
+// 64 points and walks all row blocks so |v|^2 is reduced without atomics.
+// ---------------------------------------------------------------------------------------------
+#define PB_BM 64
+#define PB_BP 64
+#define PB_BK 16
+
+template <int EMIT>   // 0 none, 1 fp64, 2 fp32(tf32-rounded)
+__global__ void __launch_bounds__(256)
+k_solve_var(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, int valid,
+            double* __restrict__ var_out, long long out_ld, void* __restrict__ vall, long long v_count) {
+  __shared__ double Ws[PB_BK][PB_BM + 1];   // +1: conflict-free transposed stores
+  __shared__ __align__(16) double Ks[PB_BK][PB_BP];
+  __shared__ double red[16][PB_BP];
+  const int g = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int np = ms.npad;
+  const double* Wg = ms.W + (size_t)g * np * np;
+  const double* Kg = Kx + (size_t)g * np * P + (size_t)blockIdx.x * PB_BP;
+  double ssum[4] = {0.0, 0.0, 0.0, 0.0};
+  const int nrb = np / PB_BM;
+  const bool emit = (EMIT != 0) && (g > 0) && (vall != nullptr);
+  for (int rb = 0; rb < nrb; ++rb) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int cmax = (rb + 1) * PB_BM;
+    for (int c0 = 0; c0 < cmax; c0 += PB_BK) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = tid + 256 * q;
+        const int r = e >> 4, c = e & 15;
+        Ws[c][r] = Wg[(size_t)(rb * PB_BM + r) * np + c0 + c];
+        const int kc = e >> 6, kp = e & 63;
+        Ks[kc][kp] = Kg[(size_t)(c0 + kc) * P + kp];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < PB_BK; ++c) {
+        const double2 k01 = *reinterpret_cast<const double2*>(&Ks[c][tx * 4]);
+        const double2 k23 = *reinterpret_cast<const double2*>(&Ks[c][tx * 4 + 2]);
+        const double w[4] = {Ws[c][ty * 4], Ws[c][ty * 4 + 1], Ws[c][ty * 4 + 2], Ws[c][ty * 4 + 3]};
+        const double kk[4] = {k01.x, k01.y, k23.x, k23.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(w[i], kk[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ssum[j] = fma(acc[i][j], acc[i][j], ssum[j]);
+    if (emit) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long pl = (long long)blockIdx.x * PB_BP + tx * 4 + j;
+        if (pl < valid) {
+          const size_t row = ((size_t)(g - 1) * v_count + p0 + pl) * np + rb * PB_BM + ty * 4;
+          if (EMIT == 1) {
+            double* o = reinterpret_cast<double*>(vall) + row;
+            *reinterpret_cast<double2*>(o) = make_double2(acc[0][j], acc[1][j]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(acc[2][j], acc[3][j]);
+          } else {
+            float* o = reinterpret_cast<float*>(vall) + row;
+            *reinterpret_cast<float4*>(o) = make_float4(to_tf32((float)acc[0][j]), to_tf32((float)acc[1][j]),
+                                                        to_tf32((float)acc[2][j]), to_tf32((float)acc[3][j]));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[ty][tx * 4 + j] = ssum[j];
+  __syncthreads();
+  if (tid < PB_BP) {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) s += red[t][tid];
+    const long long pl = (long long)blockIdx.x * PB_BP + tid;
+    if (pl < valid) {
+      const double v = fmax(0.0, ms.sf2[g] - s);                                  // GP_Safe.py:343
+      var_out[(size_t)g * out_ld + p0 + pl] = v * ms.Ystd[g] * ms.Ystd[g];        // :347
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+template <int D>
+static void launch_crosscov(sbo_ctx* ctx, const GridSpec& gs, long long p0, int P, int valid, double* Kx,
+                            double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp) {
+  dim3 grid((unsigned)cdiv(P, XC_THREADS), (unsigned)ctx->ms.G);
+  k_crosscov<D><<<grid, XC_THREADS, 0, ctx->stream>>>(ctx->ms, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax,
+                                                      grad_out, grad_gp);
+}
+
+static int crosscov_dispatch(sbo_ctx* ctx, const GridSpec& gs, long long p0, int P, int valid, double* Kx,
+                             double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp) {
+  switch (ctx->ms.d) {
+    case 1: launch_crosscov<1>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 2: launch_crosscov<2>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 3: launch_crosscov<3>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 4: launch_crosscov<4>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 5: launch_crosscov<5>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 6: launch_crosscov<6>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 7: launch_crosscov<7>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    default: launch_crosscov<8>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+  }
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
+static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, int valid, double* var_out,
+                          long long out_ld, int keep_v, void* vall, long long v_count) {
+  dim3 grid((unsigned)(P / PB_BP), (unsigned)ctx->ms.G);
+  if (keep_v == 1)
+    k_solve_var<1><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+  else if (keep_v == 2)
+    k_solve_var<2><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+  else
+    k_solve_var<0><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
+// points per chunk so that the Kx scratch stays below ~1 GiB
+static long long chunk_points(const ModelSpec& ms, long long count) {
+  const size_t per_pt = (size_t)ms.G * ms.npad * sizeof(double);
+  long long p = (long long)((size_t)1 << 30) / (long long)per_pt;
+  p = (p / 128) * 128;
+  if (p < 128) p = 128;
+  const long long need = cdiv(count, 128) * 128;
+  return p < need ? p : need;
+}
+
+int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
+  SBO_REQUIRE(ctx->have_model, "sbo_posterior: no model (call sbo_set_model)");
+  SBO_REQUIRE(ctx->have_grid, "sbo_posterior: no grid (call sbo_set_grid / sbo_set_points)");
+  SBO_REQUIRE(ctx->gs.d == ctx->ms.d, "grid and model dimensions differ");
+  SBO_REQUIRE(keep_v >= 0 && keep_v <= 2, "keep_v must be 0, 1 or 2");
+  const ModelSpec& ms = ctx->ms;
+  const long long count = ctx->gs.count;
+  SBO_REQUIRE(count > 0, "empty shard");
+  SBO_TRY(sbo_ensure(ctx, ctx->mean, sizeof(double) * (size_t)ms.G * count));
+  SBO_TRY(sbo_ensure(ctx, ctx->var, sizeof(double) * (size_t)ms.G * count));
+  SBO_TRY(sbo_ensure(ctx, ctx->lmax, sizeof(double) * SBO_MAX_G));
+  const long long P = chunk_points(ms, count);
+  SBO_TRY(sbo_ensure(ctx, ctx->kx, sizeof(double) * (size_t)ms.G * ms.npad * P));
+  ctx->keep_v = 0;
+  if (keep_v && ms.G > 1) {
+    const size_t esz = keep_v == 1 ? sizeof(double) : sizeof(float);
+    SBO_TRY(sbo_ensure(ctx, ctx->vall, esz * (size_t)(ms.G - 1) * count * ms.npad));
+  }
+  SBO_CUDA(cudaMemsetAsync(ctx->lmax.p, 0, sizeof(double) * SBO_MAX_G, ctx->stream));
+  ev_reset(ctx, 1); ev_reset(ctx, 2);
+  for (long long p0 = 0; p0 < count; p0 += P) {
+    const int valid = (int)((count - p0) < P ? (count - p0) : P);
+    const int Pc = (int)P;
+    ev_begin(ctx, 1);
+    SBO_TRY(crosscov_dispatch(ctx, ctx->gs, p0, Pc, valid, (double*)ctx->kx.p, (double*)ctx->mean.p, count,
+                              with_grad ? (double*)ctx->lmax.p : nullptr, nullptr, -1));
+    ev_end(ctx);
+    ev_begin(ctx, 2);
+    SBO_TRY(solve_dispatch(ctx, (const double*)ctx->kx.p, Pc, p0, valid, (double*)ctx->var.p, count,
+                           (ms.G > 1) ? keep_v : 0, ctx->vall.p, count));
+    ev_end(ctx);
+  }
+  if (keep_v && ms.G > 1) ctx->keep_v = keep_v;
+  ctx->have_post = true;
+  ctx->have_sets = ctx->have_sets2 = false;
+  return SBO_OK;
+}
+
+// GP_inference at arbitrary points (GP_Safe.py:310-352), used by BO.mean/ucb/lcb (SafeOpt.py:29-45)
+static int points_common(sbo_ctx* ctx, int64_t m, const double* x, GridSpec& tmp, DevBuf& xbuf) {
+  SBO_REQUIRE(ctx->have_model, "no model (call sbo_set_model)");
+  SBO_REQUIRE(m >= 1 && x, "bad points");
+  SBO_TRY(sbo_ensure(ctx, xbuf, sizeof(double) * (size_t)m * ctx->ms.d));
+  SBO_CUDA(cudaMemcpyAsync(xbuf.p, x, sizeof(double) * (size_t)m * ctx->ms.d, cudaMemcpyHostToDevice, ctx->stream));
+  tmp = GridSpec{};
+  tmp.kind = 2; tmp.d = ctx->ms.d; tmp.N = m; tmp.first = 0; tmp.count = m;
+  tmp.explicit_pts = (const double*)xbuf.p;
+  return SBO_OK;
+}
+
+int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, double* var) {
+  GridSpec tmp;
+  DevBuf &xbuf = ctx->pp_x, &mbuf = ctx->pp_m, &vbuf = ctx->pp_v, &kbuf = ctx->pp_k;
+  SBO_TRY(points_common(ctx, m, x, tmp, xbuf));
+  const ModelSpec& ms = ctx->ms;
+  SBO_TRY(sbo_ensure(ctx, mbuf, sizeof(double) * (size_t)ms.G * m));
+  SBO_TRY(sbo_ensure(ctx, vbuf, sizeof(double) * (size_t)ms.G * m));
+  const long long P = chunk_points(ms, m);
+  SBO_TRY(sbo_ensure(ctx, kbuf, sizeof(double) * (size_t)ms.G * ms.npad * P));
+  for (long long p0 = 0; p0 < m; p0 += P) {
+    const int valid = (int)((m - p0) < P ? (m - p0) : P);
+    SBO_TRY(crosscov_dispatch(ctx, tmp, p0, (int)P, valid, (double*)kbuf.p, (double*)mbuf.p, m, nullptr, nullptr, -1));
+    SBO_TRY(solve_dispatch(ctx, (const double*)kbuf.p, (int)P, p0, valid, (double*)vbuf.p, m, 0, nullptr, 0));
+  }
+  std::vector<double> hm((size_t)ms.G * m), hv((size_t)ms.G * m);
+  SBO_CUDA(cudaMemcpyAsync(hm.data(), mbuf.p, sizeof(double) * hm.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaMemcpyAsync(hv.data(), vbuf.p, sizeof(double) * hv.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t p = 0; p < m; ++p)
+    for (int g = 0; g < ms.G; ++g) {
+      if (mean) mean[p * ms.G + g] = hm[(size_t)g * m + p];
+      if (var) var[p * ms.G + g] = hv[(size_t)g * m + p];
+    }
+  return SBO_OK;
+}
+
+int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad) {
+  GridSpec tmp;
+  DevBuf &xbuf = ctx->pp_x, &gbuf = ctx->pp_g, &kbuf = ctx->pp_k;
+  SBO_REQUIRE(gp >= 0 && gp < ctx->ms.G, "gp index out of range");
+  SBO_TRY(points_common(ctx, m, x, tmp, xbuf));
+  const ModelSpec& ms = ctx->ms;
+  SBO_TRY(sbo_ensure(ctx, gbuf, sizeof(double) * (size_t)ms.d * m));
+  const long long P = chunk_points(ms, m);
+  SBO_TRY(sbo_ensure(ctx, kbuf, sizeof(double) * (size_t)ms.G * ms.npad * P));
+  for (long long p0 = 0; p0 < m; p0 += P) {
+    const int valid = (int)((m - p0) < P ? (m - p0) : P);
+    SBO_TRY(crosscov_dispatch(ctx, tmp, p0, (int)P, valid, (double*)kbuf.p, nullptr, m, nullptr, (double*)gbuf.p, gp));
+  }
+  SBO_CUDA(cudaMemcpyAsync(grad, gbuf.p, sizeof(double) * (size_t)ms.d * m, cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SBO_OK;
+}

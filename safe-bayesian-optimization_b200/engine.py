@@ -1,0 +1,298 @@
+"""GridEngine -- host-side driver of the CUDA grid pipeline (through the C ABI only).
+
+One engine = one ``sbo_ctx`` = one GPU.  It owns no numerics: every number it
+returns was produced by a kernel of libsbo_b200.so.  The reference objects it
+feeds are the drop-in classes in ``models/`` (SafeOpt.BO, GoOSE.BO).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+class SboError(RuntimeError):
+    pass
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def unpack_bits(words, count):
+    """uint32 little-endian bit words -> bool array of length count."""
+    b = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")
+    return b[:count].astype(bool)
+
+
+class GridEngine:
+    def __init__(self, device=0, stream=None):
+        self._lib = capi.load()
+        h = C.c_void_p()
+        rc = self._lib.sbo_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SboError(f"sbo_create failed ({rc}): {self._lib.sbo_last_error(None).decode()}")
+        self._h = h
+        self.device = int(device)
+        self.n = self.d = self.G = 0
+        self.N = 0
+        self.first = 0
+        self.count = 0
+        self.grid_kind = None
+        if stream is not None:
+            self._ck(self._lib.sbo_set_stream(self._h, C.c_void_p(int(stream))))
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.sbo_last_error(self._h).decode()
+            if rc == -1:
+                raise ValueError(msg)
+            raise SboError(f"libsbo_b200 error {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.sbo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        self._ck(self._lib.sbo_set_option(self._h, name.encode(), int(value)))
+
+    def kernel_launches(self, reset=False):
+        return int(self._lib.sbo_kernel_launches(self._h, 1 if reset else 0))
+
+    def phase_ms(self):
+        out = {}
+        v = C.c_double()
+        for i, nm in enumerate(capi.PHASES):
+            self._ck(self._lib.sbo_phase_ms(self._h, i, C.byref(v)))
+            out[nm] = v.value
+        return out
+
+    # -- model ------------------------------------------------------------------------------
+    def set_model(self, ds):
+        """Upload ``inference_datasets`` (models/GP_Safe.py:236-245).  invKopt is not needed."""
+        Xn, Yn, hyp = _f64(ds["X_norm"]), _f64(ds["Y_norm"]), _f64(ds["hypopt"])
+        n, d = Xn.shape
+        G = Yn.shape[1]
+        if hyp.shape != (d + 2, G):
+            raise ValueError("ERROR W and X_norm dimension should be same")   # GP_Safe.py:134-135
+        xm, xs, ym, ys = _f64(ds["X_mean"]), _f64(ds["X_std"]), _f64(ds["Y_mean"]), _f64(ds["Y_std"])
+        self._ck(self._lib.sbo_set_model(self._h, n, d, G, capi.dptr(Xn), capi.dptr(Yn), capi.dptr(xm), capi.dptr(xs),
+                                         capi.dptr(ym), capi.dptr(ys), capi.dptr(hyp)))
+        self.n, self.d, self.G = n, d, G
+
+    def get_model(self):
+        L = np.empty((self.G, self.n, self.n))
+        W = np.empty((self.G, self.n, self.n))
+        a = np.empty((self.G, self.n))
+        self._ck(self._lib.sbo_get_model(self._h, capi.dptr(L), capi.dptr(W), capi.dptr(a)))
+        return L, W, a
+
+    # -- points -----------------------------------------------------------------------------
+    def set_grid(self, lo, hi, pts):
+        lo, hi = _f64(lo), _f64(hi)
+        pts = np.ascontiguousarray(np.asarray(pts, dtype=np.int64))
+        d = lo.shape[0]
+        self._ck(self._lib.sbo_set_grid(self._h, d, pts.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(lo), capi.dptr(hi)))
+        self.N = int(np.prod(pts))
+        self.first, self.count = 0, self.N
+        self.grid_kind = "mesh"
+        self.gd = d
+        self.grid_shape = tuple(int(p) for p in pts)
+
+    def set_points(self, pts):
+        pts = _f64(pts)
+        N, d = pts.shape
+        self._ck(self._lib.sbo_set_points(self._h, N, d, capi.dptr(pts)))
+        self.N = N
+        self.first, self.count = 0, N
+        self.grid_kind = "points"
+        self.gd = d
+
+    def set_shard(self, first, count):
+        self._ck(self._lib.sbo_set_shard(self._h, int(first), int(count)))
+        self.first, self.count = int(first), int(count)
+
+    def point_coords(self, idx):
+        x = np.empty(8)
+        self._ck(self._lib.sbo_point_coords(self._h, int(idx), capi.dptr(x)))
+        return x[: self.gd].copy()
+
+    # -- posterior --------------------------------------------------------------------------
+    def posterior(self, with_grad=False, keep_v=0, fetch=True):
+        """GP posterior over the local shard.  Returns (mean, var) as (count, G) views when fetch."""
+        if fetch:
+            mean = np.empty((self.G, self.count))
+            var = np.empty((self.G, self.count))
+            self._ck(self._lib.sbo_posterior(self._h, int(with_grad), int(keep_v), capi.dptr(mean), capi.dptr(var)))
+            return mean.T, var.T
+        self._ck(self._lib.sbo_posterior(self._h, int(with_grad), int(keep_v), None, None))
+        return None
+
+    def point_posterior(self, x):
+        x = _f64(x).reshape(-1, self.d)
+        m = x.shape[0]
+        mean = np.empty((m, self.G))
+        var = np.empty((m, self.G))
+        self._ck(self._lib.sbo_point_posterior(self._h, m, capi.dptr(x), capi.dptr(mean), capi.dptr(var)))
+        return mean, var
+
+    def point_mean_grad(self, x, gp):
+        x = _f64(x).reshape(-1, self.d)
+        g = np.empty((x.shape[0], self.d))
+        self._ck(self._lib.sbo_point_mean_grad(self._h, int(gp), x.shape[0], capi.dptr(x), capi.dptr(g)))
+        return g
+
+    def lipschitz(self):
+        L = np.empty(self.G)
+        self._ck(self._lib.sbo_lipschitz(self._h, capi.dptr(L)))
+        return L
+
+    # -- sets -------------------------------------------------------------------------------
+    @staticmethod
+    def _sets_dict(r):
+        return {k: getattr(r, k) for k, _ in capi.SetsResult._fields_}
+
+    def sets(self, beta, unsafe_rule=capi.UNSAFE_ALL, strict=False):
+        r = capi.SetsResult()
+        self._ck(self._lib.sbo_sets(self._h, float(beta), int(unsafe_rule), int(bool(strict)), C.byref(r)))
+        return self._sets_dict(r)
+
+    def sets_pass1(self, beta, unsafe_rule=capi.UNSAFE_ALL, strict=False):
+        r = capi.SetsResult()
+        self._ck(self._lib.sbo_sets_pass1(self._h, float(beta), int(unsafe_rule), int(bool(strict)), C.byref(r)))
+        return self._sets_dict(r)
+
+    def sets_pass2(self, min_ucb0):
+        r = capi.SetsResult()
+        self._ck(self._lib.sbo_sets_pass2(self._h, float(min_ucb0), C.byref(r)))
+        return self._sets_dict(r)
+
+    def mask(self, kind, which=0):
+        nw = (self.count + 31) // 32
+        w = np.empty(nw, dtype=np.uint32)
+        self._ck(self._lib.sbo_get_mask(self._h, int(kind), int(which), w.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return unpack_bits(w, self.count)
+
+    def set_user_mask(self, mask_bool):
+        m = np.zeros(((self.count + 31) // 32) * 32, dtype=np.uint8)
+        m[: self.count] = np.asarray(mask_bool, dtype=np.uint8)
+        w = np.packbits(m, bitorder="little").view(np.uint32)
+        w = np.ascontiguousarray(w)
+        self._ck(self._lib.sbo_set_user_mask(self._h, w.ctypes.data_as(C.POINTER(C.c_uint32))))
+
+    def mask_dev(self, kind, which=0):
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._ck(self._lib.sbo_mask_dev(self._h, int(kind), int(which), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def posterior_dev(self):
+        m, v = C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.sbo_posterior_dev(self._h, C.byref(m), C.byref(v)))
+        return m.value, v.value
+
+    def argreduce(self, kind, mask_kind, which=0, target=None):
+        idx = C.c_int64()
+        val = C.c_double()
+        t = None
+        if target is not None:
+            tt = _f64(target)
+            t = capi.dptr(tt)
+        self._ck(self._lib.sbo_argreduce(self._h, int(kind), int(mask_kind), int(which), t, C.byref(idx), C.byref(val)))
+        return idx.value, val.value
+
+    # -- pair kernels -----------------------------------------------------------------------
+    def _pair_dict(self, r):
+        nc = max(self.G - 1, 0)
+        return {"best_idx": r.best_idx, "best_value": r.best_value,
+                "per_idx": [r.per_idx[c] for c in range(nc)], "per_value": [r.per_value[c] for c in range(nc)],
+                "n_x": r.n_x, "n_z": r.n_z, "pairs_algorithmic": r.pairs_algorithmic,
+                "pairs_evaluated": r.pairs_evaluated, "n_hit": r.n_hit}
+
+    def expander(self, beta, L=None, mode=capi.MODE_LIPSCHITZ, precision=capi.PREC_FP64, want_counts=False):
+        r = capi.PairResult()
+        Lp = None
+        if L is not None:
+            Lc = _f64(L)
+            if Lc.shape[0] != self.G:
+                raise ValueError("L must have one entry per GP")
+            Lp = capi.dptr(Lc)
+        counts = None
+        cp = None
+        if want_counts and mode == capi.MODE_FANTASY:
+            counts = np.zeros(self.count, dtype=np.int32)
+            cp = counts.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self._lib.sbo_expander(self._h, int(mode), int(precision), float(beta), Lp, C.byref(r), cp))
+        out = self._pair_dict(r)
+        if counts is not None:
+            out["counts"] = counts
+        return out
+
+    def goose_target(self, beta, L):
+        r = capi.PairResult()
+        Lc = _f64(L)
+        if Lc.shape[0] != self.G:
+            raise ValueError("L must have one entry per GP")
+        self._ck(self._lib.sbo_goose_target(self._h, float(beta), capi.dptr(Lc), C.byref(r)))
+        return self._pair_dict(r)
+
+    # -- whole steps (drivers' decision rules) ------------------------------------------------
+    def safeopt_step(self, ds, beta, mode="lipschitz", precision="fp64", unsafe_rule=capi.UNSAFE_ALL, L=None,
+                     upload=True):
+        """model upload -> posterior -> sets -> L -> expander pairs -> arg-reductions -> x_new.
+        Decision rule of test/test_SafeOpt.py:144-158.  Returns a dict of scalars/indices."""
+        if upload:
+            self.set_model(ds)
+        fantasy = mode == "fantasy"
+        prec = capi.PREC_TF32 if precision == "tf32" else capi.PREC_FP64
+        keep_v = 0 if not fantasy else (2 if prec == capi.PREC_TF32 else 1)
+        self.posterior(with_grad=not fantasy and L is None, keep_v=keep_v, fetch=False)
+        s = self.sets(beta, unsafe_rule)
+        out = dict(s)
+        out["minimizer_std"] = float(np.sqrt(s["minimizer_var"])) if s["minimizer_idx"] >= 0 else 0.0
+        if fantasy:
+            ex = self.expander(beta, None, capi.MODE_FANTASY, prec)
+        else:
+            if L is None:
+                Lg = self.lipschitz()
+                L = np.full(self.G, Lg[self.G - 1])       # SafeOpt.py:110: L of constraint n_fun-1 for every idx
+                out["L"] = Lg
+            ex = self.expander(beta, L, capi.MODE_LIPSCHITZ, prec)
+        out["expander"] = ex
+        out["expander_idx"] = ex["best_idx"]
+        out["expander_std"] = float(np.sqrt(ex["best_value"])) if ex["best_idx"] >= 0 else 0.0
+        out["x_new_idx"] = s["minimizer_idx"] if out["minimizer_std"] > out["expander_std"] else ex["best_idx"]
+        return out
+
+    def goose_step(self, ds, beta, unsafe_rule=capi.UNSAFE_ALL, L=None, upload=True):
+        """Decision rule of test/test_GoOSE.py:151-162."""
+        if upload:
+            self.set_model(ds)
+        self.posterior(with_grad=L is None, keep_v=0, fetch=False)
+        s = self.sets_pass1(beta, unsafe_rule)
+        out = dict(s)
+        if L is None:
+            Lg = self.lipschitz()
+            L = np.full(self.G, Lg[self.G - 1])           # GoOSE.py:100
+            out["L"] = Lg
+        tg = self.goose_target(beta, L)
+        out["target"] = tg
+        out["target_idx"], out["target_lcb"] = tg["best_idx"], tg["best_value"]
+        if s["min_lcb0"] <= tg["best_value"] or tg["best_idx"] < 0:
+            out["x_new_idx"] = s["min_lcb0_idx"]
+            out["explore_idx"] = -1
+        else:
+            e_idx, _ = self.argreduce(capi.ARGMIN_DIST, capi.MASK_SAFE, 0, self.point_coords(tg["best_idx"]))
+            out["x_new_idx"] = e_idx
+            out["explore_idx"] = e_idx
+        return out

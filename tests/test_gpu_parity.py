@@ -1,0 +1,430 @@
+"""GPU parity tests: the CUDA grid pipeline (called through the C ABI) vs the NumPy oracle on the same
+seeded inputs, and vs the committed golden fixtures at the reference's full 400x400 grid.
+
+Tolerances (stated scale-relatively):
+  posterior   |d mean| <= TOL * max|mean| (per GP),  |d var| <= TOL * sf2 * Ystd^2
+              TOL = 1e-10 vs the Cholesky-form oracle, 2e-8 vs the reference's inverse form
+              (the two FP64 formulations themselves differ by ~4e-10 at cond(K) ~ 1e7)
+  sets        identical except points whose bound lies within SET_TOL*scale of the threshold
+  arg-reductions  identical grid index, or (near-ties) an index whose oracle score is within
+              1e-9 relative of the optimum
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_ds
+
+pytestmark = pytest.mark.gpu
+
+TOL_CHOL = 1e-10
+TOL_INV = 2e-8
+SET_TOL = 1e-8
+
+
+def _capi():
+    from sbo_b200 import _capi
+    return _capi
+
+
+def post_err(oracle, ds, m, v, mo, vo):
+    d = ds["X_norm"].shape[1]
+    em, ev = 0.0, 0.0
+    for i in range(m.shape[1]):
+        _, sf2, _ = oracle.unpack_hyper(ds["hypopt"][:, i], d)
+        em = max(em, np.max(np.abs(m[:, i] - mo[:, i])) / max(np.max(np.abs(mo[:, i])), ds["Y_std"][i]))
+        ev = max(ev, np.max(np.abs(v[:, i] - vo[:, i])) / (sf2 * ds["Y_std"][i] ** 2))
+    return em, ev
+
+
+def check_mask(got, want, margin, scale, what):
+    """got/want bool masks; margin = |bound - threshold| per point.  Mismatches only where ambiguous."""
+    bad = got != want
+    if bad.any():
+        assert np.all(margin[bad] <= SET_TOL * scale), f"{what}: {bad.sum()} mismatches beyond tolerance"
+    return int(bad.sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# model
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4, 14, 35, 70, 200])
+def test_model_factorisation(engine, oracle, c3, n):
+    rng = np.random.default_rng(n)
+    if n <= 35:
+        X, Y, hyp = c3["X"][:n], c3["Y"][:n], c3[f"hyp_{35 if n > 20 else (20 if n > 5 else 5)}"]
+    else:
+        X = rng.uniform([4, 70], [7, 100], size=(n, 2))
+        Y = np.column_stack([np.sin(X[:, 0]) * X[:, 1], 0.1 - 0.01 * X[:, 0], 0.05 + 0.001 * X[:, 1]])
+        hyp = c3["hyp_35"]
+    ds = oracle.make_inference_datasets(X, Y, hyp)
+    engine.set_model(ds)
+    L, W, alpha = engine.get_model()
+    fac = oracle.chol_factors(ds)
+    for i in range(3):
+        Lo, ao = fac[i]
+        K = oracle.build_K(ds["X_norm"], ds["hypopt"][:, i])
+        assert np.max(np.abs(L[i] @ L[i].T - K)) <= 1e-12 * np.max(np.abs(K))
+        assert np.max(np.abs(L[i] - Lo)) <= 1e-10 * np.max(np.abs(Lo))
+        assert np.max(np.abs(W[i] @ Lo - np.eye(n))) <= 1e-9
+        assert np.max(np.abs(alpha[i] - ao)) <= 1e-8 * max(1.0, np.max(np.abs(ao)))
+
+
+def test_not_positive_definite_is_an_error(engine, oracle, c1):
+    import sbo_b200
+    ds = golden_ds(oracle, c1, 4)
+    ds = dict(ds)
+    ds["X_norm"] = np.vstack([ds["X_norm"], ds["X_norm"][:1]])          # duplicated input ...
+    ds["Y_norm"] = np.vstack([ds["Y_norm"], ds["Y_norm"][:1]])
+    hyp = ds["hypopt"].copy()
+    hyp[3, :] = -30.0                                                   # ... and (almost) no noise
+    hyp[2, :] = 6.0
+    ds["hypopt"] = hyp
+    try:
+        engine.set_model(ds)                                            # eps_f32*I may or may not rescue it
+    except sbo_b200.SboError as e:
+        assert "positive definite" in str(e)
+    engine.set_model(golden_ds(oracle, c1, 4))                          # the context stays usable
+
+
+# ------------------------------------------------------------------------------------------------
+# posterior on the reference's grids (C1 Benoit, C3 WOR; 400 x 400)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n", [("c1", 4), ("c1", 9), ("c1", 14), ("c3", 5), ("c3", 20), ("c3", 35)])
+def test_posterior_full_grid(engine, oracle, request, name, n):
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    engine.set_model(ds)
+    engine.set_grid(gold["lo"], gold["hi"], [400, 400])
+    m, v = engine.posterior()
+    assert m.shape == (160000, ds["Y_norm"].shape[1]) and np.all(v >= 0)
+    pts = oracle.make_grid(gold["lo"], gold["hi"], [400, 400])
+    mb, vb = oracle.posterior_chol(pts, ds)
+    em, ev = post_err(oracle, ds, m, v, mb, vb)
+    assert em <= TOL_CHOL and ev <= TOL_CHOL, (em, ev)
+    ma, va = oracle.posterior_inv(pts, ds)
+    em, ev = post_err(oracle, ds, m, v, ma, va)
+    assert em <= TOL_INV and ev <= TOL_INV, (em, ev)
+
+
+@pytest.mark.parametrize("name,sizes", [("c1", [4, 9, 14]), ("c3", [5, 20, 35])])
+def test_point_posterior_golden(engine, oracle, request, name, sizes):
+    # the points the reference's scripts print at (test_SafeOpt.py:47, test_GP_Safe.py:25,28,44)
+    gold = request.getfixturevalue(name)
+    for n in sizes:
+        ds = golden_ds(oracle, gold, n)
+        engine.set_model(ds)
+        m, v = engine.point_posterior(gold["test_points"])
+        em, ev = post_err(oracle, ds, m, v, gold[f"tp_mean_{n}"], gold[f"tp_var_{n}"])
+        assert em <= TOL_INV and ev <= TOL_INV, (n, em, ev)
+
+
+def test_explicit_points_and_ragged_sizes(engine, oracle, c3):
+    ds = golden_ds(oracle, c3, 20)
+    engine.set_model(ds)
+    rng = np.random.default_rng(3)
+    for N in [1, 31, 33, 64, 1000, 4097]:
+        pts = rng.uniform(c3["lo"], c3["hi"], size=(N, 2))
+        engine.set_points(pts)
+        m, v = engine.posterior()
+        mb, vb = oracle.posterior_chol(pts, ds)
+        em, ev = post_err(oracle, ds, m, v, mb, vb)
+        assert em <= TOL_CHOL and ev <= TOL_CHOL, (N, em, ev)
+        mp, vp = engine.point_posterior(pts[: min(N, 7)])
+        assert np.max(np.abs(mp - m[: min(N, 7)])) == 0.0 and np.max(np.abs(vp - v[: min(N, 7)])) == 0.0
+
+
+def test_properties_reference_prints(engine, oracle, c1):
+    ds = golden_ds(oracle, c1, 9)
+    engine.set_model(ds)
+    m, v = engine.point_posterior(c1["X"][:9])          # interpolation, test_GP_Safe.py:33-41
+    assert np.max(np.abs(m - c1["Y"][:9])) < 0.05 and np.max(v) < 1e-2
+    m, v = engine.point_posterior(np.array([[10.0, 10.0]]))   # constraint prior, test_GP_Safe.py:43-47
+    assert m[0, 1] == pytest.approx(-ds["Y_mean"][1], rel=1e-6)
+
+
+def test_mean_gradient_and_lipschitz(engine, oracle, c3):
+    ds = golden_ds(oracle, c3, 20)
+    engine.set_model(ds)
+    x = np.array([[6.0, 85.0], [5.1, 78.0], [4.2, 99.0]])
+    for i in range(3):
+        g = engine.point_mean_grad(x, i)
+        go = oracle.mean_grad(x, ds, i)
+        assert np.max(np.abs(g - go)) <= 1e-9 * max(1.0, np.max(np.abs(go)))
+    engine.set_grid(c3["lo"], c3["hi"], [150, 150])
+    engine.posterior(with_grad=True, fetch=False)
+    L = engine.lipschitz()
+    pts = oracle.make_grid(c3["lo"], c3["hi"], [150, 150])
+    for i in range(3):
+        assert L[i] == pytest.approx(oracle.lipschitz_constant(pts, ds, i), rel=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# sets + arg-reductions on the full reference grid
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,beta", [("c1", 4, 3.0), ("c1", 9, 3.0), ("c1", 14, 3.0),
+                                          ("c3", 5, 2.0), ("c3", 20, 2.0), ("c3", 35, 2.0)])
+@pytest.mark.parametrize("rule", ["all", "any"])
+def test_sets_full_grid(engine, oracle, request, name, n, beta, rule):
+    capi = _capi()
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    engine.set_model(ds)
+    engine.set_grid(gold["lo"], gold["hi"], [400, 400])
+    m, v = engine.posterior()
+    s = engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
+    # oracle sets from the oracle's own posterior (inverse form = the reference's)
+    pts = oracle.make_grid(gold["lo"], gold["hi"], [400, 400])
+    mo, vo = oracle.posterior_inv(pts, ds)
+    lcb, ucb = oracle.bounds(mo, vo, beta)
+    S, Z = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, rule)
+    scale = float(np.max(ds["Y_std"][1:]))
+    cmargin = np.min(np.abs(lcb[:, 1:]), axis=1)
+    nS = check_mask(engine.mask(capi.MASK_SAFE), S, cmargin, scale, "S")
+    nZ = check_mask(engine.mask(capi.MASK_UNSAFE), Z, cmargin, scale, "Z")
+    assert abs(s["n_safe"] - S.sum()) <= nS and abs(s["n_unsafe"] - Z.sum()) <= nZ
+    # same sets from the GPU's own posterior must be bit-identical (bounds are FMA-free on both sides)
+    lg, ug = oracle.bounds(m, v, beta)
+    assert np.array_equal(engine.mask(capi.MASK_SAFE), oracle.safe_mask(lg))
+    assert np.array_equal(engine.mask(capi.MASK_UNSAFE), oracle.unsafe_mask(lg, rule))
+    i_u, v_u = oracle.minimize_obj_ucb(ug, oracle.safe_mask(lg))
+    i_l, v_l = oracle.minimize_obj_lcb(lg, oracle.safe_mask(lg))
+    assert (s["min_ucb0_idx"], s["min_lcb0_idx"]) == (i_u, i_l)
+    if i_u >= 0:
+        assert s["min_ucb0"] == v_u and s["min_lcb0"] == v_l
+    mi, mstd, M, _ = oracle.minimizer(v, lg, ug, oracle.safe_mask(lg))
+    assert np.array_equal(engine.mask(capi.MASK_MIN), M) and s["n_min"] == M.sum() and s["minimizer_idx"] == mi
+    # golden summary (oracle inverse form at the full grid, rule 'all'): sizes within the ambiguous count
+    if rule == "all":
+        g = gold[f"summary_{n}"]
+        assert abs(s["n_safe"] - g[0]) <= nS + 2 and abs(s["n_unsafe"] - g[2]) <= nZ + 2
+        sc = gold[f"scalars_{n}"]
+        assert s["min_ucb0"] == pytest.approx(sc[0], rel=1e-7, abs=1e-9)
+        assert np.sqrt(s["minimizer_var"]) == pytest.approx(sc[1], rel=1e-6)
+        # chosen minimiser: identical index unless the oracle's optimum is a near-tie
+        if s["minimizer_idx"] != g[3]:
+            assert vo[s["minimizer_idx"], 0] >= vo[g[3], 0] * (1 - 1e-9)
+
+
+def test_sets_strict_and_plot_mask(engine, oracle, c1):
+    capi = _capi()
+    ds = golden_ds(oracle, c1, 9)
+    engine.set_model(ds)
+    engine.set_grid(c1["lo"], c1["hi"], [400, 400])
+    m, v = engine.posterior()
+    engine.sets(3.0, capi.UNSAFE_ALL, strict=True)
+    want = (m[:, 1] - 3.0 * np.sqrt(v[:, 1])) > 0.0          # test/test_SafeOpt.py:337-338
+    assert np.array_equal(engine.mask(capi.MASK_SAFE), want)
+
+
+def test_empty_sets_and_no_constraints(engine, oracle, c1):
+    capi = _capi()
+    ds = golden_ds(oracle, c1, 4)
+    engine.set_model(ds)
+    engine.set_grid([5.0, 5.0], [6.0, 6.0], [9, 7])             # far from the data: S is empty
+    engine.posterior(with_grad=True, fetch=False)
+    s = engine.sets(3.0)
+    assert s["n_safe"] == 0 and s["min_ucb0_idx"] == -1 and s["minimizer_idx"] == -1 and s["n_min"] == 0
+    ex = engine.expander(3.0, np.array([1.0, 1.0]))
+    assert ex["best_idx"] == -1 and ex["n_x"] == 0
+    tg = engine.goose_target(3.0, np.array([1.0, 1.0]))
+    assert tg["best_idx"] == -1
+    st = engine.safeopt_step(ds, 3.0)
+    assert st["x_new_idx"] == -1
+    # G = 1: objective only -> every point is safe, there is no unsafe set
+    ds1 = oracle.make_inference_datasets(c1["X"][:9], c1["Y"][:9, :1], c1["hyp_9"][:, :1])
+    engine.set_model(ds1)
+    engine.set_grid(c1["lo"], c1["hi"], [50, 30])
+    engine.posterior(fetch=False)
+    s = engine.sets(3.0)
+    assert s["n_safe"] == 1500 and s["n_unsafe"] == 0 and s["minimizer_idx"] >= 0
+
+
+# ------------------------------------------------------------------------------------------------
+# Lipschitz-mode pair kernels vs the oracle's all-pairs brute force (reduced grids: the oracle is O(|S||Z|))
+# ------------------------------------------------------------------------------------------------
+def _pair_inputs(engine, oracle, gold, n, beta, pts_per_dim, rule="all"):
+    capi = _capi()
+    ds = golden_ds(oracle, gold, n)
+    engine.set_model(ds)
+    engine.set_grid(gold["lo"], gold["hi"], pts_per_dim)
+    m, v = engine.posterior(with_grad=True)
+    s = engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
+    pts = oracle.make_grid(gold["lo"], gold["hi"], pts_per_dim)
+    lcb, ucb = oracle.bounds(m, v, beta)
+    return ds, pts, m, v, lcb, ucb, oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, rule), s
+
+
+@pytest.mark.parametrize("name,n,beta,grid", [("c1", 4, 3.0, [90, 70]), ("c1", 9, 3.0, [101, 77]), ("c1", 14, 3.0, [64, 64]),
+                                               ("c3", 5, 2.0, [80, 80]), ("c3", 20, 2.0, [75, 90]), ("c3", 35, 2.0, [60, 60])])
+def test_expander_and_target_lipschitz(engine, oracle, request, name, n, beta, grid):
+    capi = _capi()
+    gold = request.getfixturevalue(name)
+    ds, pts, m, v, lcb, ucb, S, Z, s = _pair_inputs(engine, oracle, gold, n, beta, grid)
+    G = m.shape[1]
+    Lg = engine.lipschitz()
+    # two regimes: the reference's L (max-gradient; nearly every safe point qualifies) and a 5x larger,
+    # discriminating one
+    for mult in [1.0, 5.0]:
+        L = np.full(G, Lg[G - 1] * mult)
+        ex = engine.expander(beta, L)
+        exo = oracle.expander_lipschitz(pts, S, Z, ucb, v, L)
+        for c in range(G - 1):
+            got = engine.mask(capi.MASK_EXPANDER, c)
+            bad = got != exo["masks"][c]
+            assert bad.sum() <= 2, (mult, c, bad.sum())        # only exact-threshold rounding may differ
+        assert ex["n_x"] == S.sum() and ex["n_z"] == Z.sum()
+        assert ex["pairs_algorithmic"] == S.sum() * Z.sum() * (G - 1)
+        if exo["best_idx"] >= 0 and not any((engine.mask(capi.MASK_EXPANDER, c) != exo["masks"][c]).any() for c in range(G - 1)):
+            assert ex["best_idx"] == exo["best_idx"]
+            assert np.sqrt(ex["best_value"]) == pytest.approx(exo["best_std"], rel=1e-12)
+            assert ex["per_idx"] == [p for p, _ in exo["per_idx"]]
+        tg = engine.goose_target(beta, L)
+        tgo = oracle.goose_target(pts, S, Z, ucb, lcb, L)
+        same = True
+        for c in range(G - 1):
+            bad = engine.mask(capi.MASK_TARGET, c) != tgo["masks"][c]
+            assert bad.sum() <= 2, (mult, c, bad.sum())
+            same = same and not bad.any()
+        if same:
+            assert tg["best_idx"] == tgo["best_idx"]
+            if tgo["best_idx"] >= 0:
+                assert tg["best_value"] == tgo["best_lcb"]
+                e_idx, dist = engine.argreduce(capi.ARGMIN_DIST, capi.MASK_SAFE, 0, pts[tgo["best_idx"]])
+                eo, do = oracle.explore_safeset(pts, S, pts[tgo["best_idx"]])
+                assert e_idx == eo and dist == pytest.approx(do, rel=1e-14)
+
+
+@pytest.mark.parametrize("name,n,beta", [("c1", 9, 3.0), ("c3", 20, 2.0)])
+def test_whole_steps_match_oracle(engine, oracle, request, name, n, beta):
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    grid = [72, 56]
+    engine.set_grid(gold["lo"], gold["hi"], grid)
+    pts = oracle.make_grid(gold["lo"], gold["hi"], grid)
+    st = engine.safeopt_step(ds, beta)
+    so = oracle.safeopt_step(pts, ds, beta, form="chol")
+    assert st["n_safe"] == so["S"].sum() and st["n_min"] == so["M"].sum()
+    assert st["minimizer_idx"] == so["minimizer_idx"] and st["expander_idx"] == so["expander_idx"]
+    assert st["x_new_idx"] == so["x_new_idx"]
+    assert st["L"][-1] == pytest.approx(so["L"][-1], rel=1e-9)
+    gs = engine.goose_step(ds, beta)
+    go = oracle.goose_step(pts, ds, beta, form="chol")
+    assert gs["min_lcb0_idx"] == go["safe_min_idx"] and gs["target_idx"] == go["target_idx"]
+    assert gs["x_new_idx"] == go["x_new_idx"]
+
+
+def test_full_grid_step_vs_golden_summary(engine, oracle, c1, c3):
+    # full 400x400 Lipschitz steps against the committed oracle summaries (make_golden.py)
+    for gold, n, beta in [(c1, 9, 3.0), (c1, 14, 3.0), (c3, 20, 2.0)]:
+        ds = golden_ds(oracle, gold, n)
+        engine.set_grid(gold["lo"], gold["hi"], [400, 400])
+        st = engine.safeopt_step(ds, beta)
+        g, sc = gold[f"summary_{n}"], gold[f"scalars_{n}"]
+        assert abs(st["n_safe"] - g[0]) <= 3 and abs(st["n_min"] - g[1]) <= 3
+        assert st["L"][-1] == pytest.approx(sc[3], rel=1e-7)
+        assert st["expander_std"] == pytest.approx(sc[2], rel=1e-6)
+        assert st["minimizer_std"] == pytest.approx(sc[1], rel=1e-6)
+        assert st["x_new_idx"] == g[5] or st["expander_std"] == pytest.approx(sc[2], rel=1e-9)
+        gs = engine.goose_step(ds, beta)
+        assert gs["min_lcb0"] == pytest.approx(sc[4], rel=1e-7, abs=1e-9)
+        assert gs["target_lcb"] == pytest.approx(sc[5], rel=1e-7, abs=1e-9)
+        assert gs["min_lcb0_idx"] == g[6] and gs["target_idx"] == g[7] and gs["x_new_idx"] == g[8]
+
+
+# ------------------------------------------------------------------------------------------------
+# fantasy expander, FP64 kernel vs oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,beta,grid,rule", [("c1", 9, 3.0, [40, 36], "all"), ("c3", 20, 2.0, [33, 47], "any"),
+                                                    ("c3", 35, 2.0, [30, 30], "all")])
+def test_fantasy_fp64_counts(engine, oracle, request, name, n, beta, grid, rule):
+    capi = _capi()
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    engine.set_model(ds)
+    engine.set_grid(gold["lo"], gold["hi"], grid)
+    m, v = engine.posterior(keep_v=1)
+    engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
+    ex = engine.expander(beta, None, capi.MODE_FANTASY, capi.PREC_FP64, want_counts=True)
+    pts = oracle.make_grid(gold["lo"], gold["hi"], grid)
+    lcb, _ = oracle.bounds(m, v, beta)
+    S, Z = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, rule)
+    want = oracle.fantasy_counts(pts, ds, beta, S, Z)
+    margin = oracle.fantasy_margin(pts, ds, beta, S, Z)                 # (|Z|,|S|)
+    amb = (np.abs(margin) <= 1e-9).sum(axis=0)                          # pairs within tolerance of the threshold
+    diff = np.abs(ex["counts"][S].astype(np.int64) - want[S])
+    assert np.all(diff <= amb), (diff.max(), amb.max())
+    assert (ex["counts"][~S] == 0).all()
+    assert ex["pairs_algorithmic"] == S.sum() * Z.sum() * (m.shape[1] - 1)
+    if not diff.any():
+        eo = oracle.expander_fantasy(pts, ds, beta, S, Z, v)
+        assert ex["best_idx"] == eo["best_idx"] and ex["n_hit"] == eo["mask"].sum()
+        assert np.array_equal(engine.mask(capi.MASK_EXPANDER, 0), eo["mask"])
+
+
+# ------------------------------------------------------------------------------------------------
+# higher-dimensional synthetic recipe (C4/C5 family) at a size the oracle finishes in seconds,
+# and size-independent properties at the full C4 size
+# ------------------------------------------------------------------------------------------------
+def test_synthetic_small_all_stages(engine, oracle):
+    from sbo_b200 import workloads
+    capi = _capi()
+    ds, lo, hi, pts_per_dim, beta = workloads.small(d=3, pts_per_dim=14, n=70, seed=7, G=3)
+    dso = dict(ds)
+    dso["invKopt"] = [np.linalg.inv(oracle.build_K(ds["X_norm"], ds["hypopt"][:, i])) for i in range(3)]
+    engine.set_model(ds)
+    engine.set_grid(lo, hi, pts_per_dim)
+    m, v = engine.posterior(with_grad=True, keep_v=1)
+    pts = oracle.make_grid(lo, hi, pts_per_dim)
+    mb, vb = oracle.posterior_chol(pts, dso)
+    em, ev = post_err(oracle, dso, m, v, mb, vb)
+    assert em <= TOL_CHOL and ev <= TOL_CHOL
+    s = engine.sets(beta, capi.UNSAFE_ANY)
+    lcb, ucb = oracle.bounds(m, v, beta)
+    S, Z = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, "any")
+    assert s["n_safe"] == S.sum() > 0 and s["n_unsafe"] == Z.sum() > 0
+    L = np.full(3, 4.0 * engine.lipschitz()[2])
+    ex = engine.expander(beta, L)
+    exo = oracle.expander_lipschitz(pts, S, Z, ucb, v, L)
+    for c in range(2):
+        assert (engine.mask(capi.MASK_EXPANDER, c) != exo["masks"][c]).sum() <= 2
+    fz = engine.expander(beta, None, capi.MODE_FANTASY, capi.PREC_FP64, want_counts=True)
+    want = oracle.fantasy_counts(pts, dso, beta, S, Z)
+    amb = (np.abs(oracle.fantasy_margin(pts, dso, beta, S, Z)) <= 1e-9).sum(axis=0)
+    assert np.all(np.abs(fz["counts"][S].astype(np.int64) - want[S]) <= amb)
+
+
+def test_c4_full_size_properties(engine, oracle):
+    """BASELINE config C4 at full size (N = 2^20, n = 512, G = 4): properties that need no O(N n^2) oracle."""
+    from sbo_b200 import workloads
+    capi = _capi()
+    ds, lo, hi, pts_per_dim, beta = workloads.c4()
+    engine.set_model(ds)
+    engine.set_grid(lo, hi, pts_per_dim)
+    m, v = engine.posterior(with_grad=True)
+    assert m.shape == (1 << 20, 4) and np.all(np.isfinite(m)) and np.all(v >= 0)
+    sf2 = 1.0
+    assert np.all(v <= sf2 * ds["Y_std"] ** 2 * (1 + 1e-12))            # posterior variance <= prior variance
+    # a random sample of grid points against the oracle (Cholesky form)
+    rng = np.random.default_rng(11)
+    idx = np.sort(rng.choice(1 << 20, size=3000, replace=False))
+    pts = np.stack([engine.point_coords(i) for i in idx])
+    dso = dict(ds)
+    mb, vb = oracle.posterior_chol(pts, dso)
+    em, ev = post_err(oracle, dso, m[idx], v[idx], mb, vb)
+    assert em <= TOL_CHOL and ev <= TOL_CHOL, (em, ev)
+    # sets: popcounts agree with the masks, M subset of S, Z disjoint from S; idempotence
+    s1 = engine.sets(beta)
+    S, Z, M = engine.mask(capi.MASK_SAFE), engine.mask(capi.MASK_UNSAFE), engine.mask(capi.MASK_MIN)
+    assert s1["n_safe"] == S.sum() and s1["n_unsafe"] == Z.sum() and s1["n_min"] == M.sum()
+    assert not (M & ~S).any() and not (S & Z).any()
+    assert 0.03 < S.mean() < 0.4
+    s2 = engine.sets(beta)
+    assert s1 == s2
+    # far-from-data prior: the constraint mean tends to -Y_mean (GP_Safe.py:331)
+    far, _ = engine.point_posterior(np.full((1, 4), 50.0))
+    assert np.allclose(far[0, 1:], -ds["Y_mean"][1:], rtol=1e-9)
+    # interpolation at the training inputs
+    Xraw = ds["X_norm"] * ds["X_std"] + ds["X_mean"]
+    Yraw = ds["Y_norm"] * ds["Y_std"] + ds["Y_mean"]
+    mt, vt = engine.point_posterior(Xraw)
+    assert np.max(np.abs(mt - Yraw) / ds["Y_std"]) < 0.2 and np.max(vt / ds["Y_std"] ** 2) < 0.05
