@@ -49,7 +49,7 @@ enum sbo_status {
 enum sbo_unsafe_rule { SBO_UNSAFE_ALL = 0, SBO_UNSAFE_ANY = 1 };
 
 enum sbo_expander_mode { SBO_MODE_LIPSCHITZ = 0, SBO_MODE_FANTASY = 1 };
-enum sbo_precision { SBO_PREC_FP64 = 0, SBO_PREC_TF32 = 1 };
+enum sbo_precision { SBO_PREC_FP64 = 0, SBO_PREC_TF32 = 1, SBO_PREC_TF32X3 = 2 };
 
 /* score selectors for sbo_argreduce */
 enum sbo_reduce_kind {
@@ -95,7 +95,8 @@ int sbo_point_coords(sbo_ctx* ctx, int64_t global_idx, double* x /* d */);
  * mean/var: [G*count] GP-major, raw (un-normalised) units, var clamped >= 0; NULL = keep on device.
  * with_grad != 0 also accumulates L_i = max_p ||grad mu_i(p)||_inf  (SafeOpt.py:68-83).
  * keep_v != 0 keeps V_i = L_i^-1 K_i(X, .) for the fantasy expander (constraints only):
- *   1 = FP64 rows, 2 = FP32 rows (TF32 operand). */
+ *   1 = FP64 rows, 2 = FP32 rows rounded to TF32 (tensor-core operand), 3 = split-TF32 rows [hi | lo]
+ *   (three-pass TF32 GEMM, ~FP32 accuracy). */
 int sbo_posterior(sbo_ctx* ctx, int with_grad, int keep_v, double* mean, double* var);
 /* GP_inference at m arbitrary points (the single-point API behind BO.mean/ucb/lcb,
  * SafeOpt.py:29-45): x[m*d] row-major -> mean[m*G], var[m*G] POINT-major like the reference. */
@@ -136,7 +137,8 @@ int sbo_argreduce(sbo_ctx* ctx, int reduce_kind, int mask_kind, int which, const
  *   constraint idx (the reference passes L_{G-1} for every idx, SafeOpt.py:110).
  * Fantasy mode (north_star, not in the reference): rank-1 posterior update of every constraint GP with
  *   the observation ucb_i(x); z is newly safe if every updated lcb_i(z) >= 0; g(x) = #newly-safe z.
- *   precision: FP64 (SIMT reference kernel) or TF32 (tcgen05/TMEM GEMM, FP32 accumulate).
+ *   precision: FP64 (SIMT reference kernel), TF32 (tcgen05/TMEM GEMM, FP32 accumulate) or TF32X3
+ *   (same kernel over split operands: x_hi.z_hi + x_hi.z_lo + x_lo.z_hi).
  */
 typedef struct sbo_pair_result {
   int64_t best_idx;  double best_value;          /* SafeOpt: argmax var_0 (value = var_0); GoOSE: argmin lcb_0 */

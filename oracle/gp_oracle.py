@@ -413,6 +413,13 @@ def fantasy_terms(points, ds, beta, factors=None):
     return mu_n, var_n, Vs, xn
 
 
+def round_tf32(a):
+    """Round float32 values to TF32 (10-bit mantissa) like PTX cvt.rna.tf32.f32: nearest, ties away from zero."""
+    b = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    b = (b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)
+    return b.view(np.float32)
+
+
 def fantasy_counts(points, ds, beta, S, Z, block=256, dtype=np.float64):
     """For every candidate x in S and every z in Z: fantasise the observation
     y_i = ucb_i(x) for each constraint GP i>=1 (noise sn2_i + eps_f32, the diagonal
@@ -422,7 +429,7 @@ def fantasy_counts(points, ds, beta, S, Z, block=256, dtype=np.float64):
         s2'_i = sigma_i^2(z) - c_i^2 / (sigma_i^2(x) + sn2_i)
         newly safe  <=>  mu'_i - beta*sqrt(max(s2'_i,0)) >= 0  for all i>=1.
     Returns counts g(x) (int64, length N, zero outside S).  ``dtype`` selects the
-    precision of the V.V^T contraction only (float32 emulates the TF32/FP32 path loosely)."""
+    precision of the V.V^T contraction only ("tf32" emulates the tensor-core operands: V rounded to TF32)."""
     N, d = points.shape
     G = ds["Y_norm"].shape[1]
     mu_n, var_n, Vs, xn = fantasy_terms(points, ds, beta)
@@ -439,7 +446,11 @@ def fantasy_counts(points, ds, beta, S, Z, block=256, dtype=np.float64):
             ell, sf2, sn2 = unpack_hyper(hyp[:, i], d)
             sn2 = sn2 + EPS_F32
             kzx = sf2 * np.exp(-0.5 * sq_dist_direct(xn[zs], xn[xb], ell))           # (|Z|,B)
-            c = kzx - (Vs[i][zs].astype(dtype) @ Vs[i][xb].astype(dtype).T).astype(np.float64)
+            if dtype == "tf32":      # operands rounded to TF32, exact products, wide accumulation
+                acc = round_tf32(Vs[i][zs]).astype(np.float64) @ round_tf32(Vs[i][xb]).astype(np.float64).T
+            else:
+                acc = (Vs[i][zs].astype(dtype) @ Vs[i][xb].astype(dtype).T).astype(np.float64)
+            c = kzx - acc
             denom = var_n[xb, i] + sn2
             mu_p = mu_n[zs, i][:, None] + c * (beta * np.sqrt(var_n[xb, i]) / denom)[None, :]
             s2_p = var_n[zs, i][:, None] - c * c / denom[None, :]

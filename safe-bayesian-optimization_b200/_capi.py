@@ -15,7 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libsbo_b200.so")
 MAX_D, MAX_G = 8, 8
 UNSAFE_ALL, UNSAFE_ANY = 0, 1
 MODE_LIPSCHITZ, MODE_FANTASY = 0, 1
-PREC_FP64, PREC_TF32 = 0, 1
+PREC_FP64, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+# precision name -> (sbo_precision, keep_v of sbo_posterior) for the fantasy expander
+PRECISIONS = {"fp64": (0, 1), "tf32": (1, 2), "tf32x3": (2, 3)}
 ARGMAX_VAR0, ARGMIN_LCB0, ARGMIN_UCB0, ARGMIN_DIST = 0, 1, 2, 3
 MASK_SAFE, MASK_MIN, MASK_UNSAFE, MASK_USER, MASK_EXPANDER, MASK_TARGET = 0, 1, 2, 3, 4, 5
 PHASES = ("model", "crosscov", "solve", "sets", "pairs", "argreduce", "pair_prep")

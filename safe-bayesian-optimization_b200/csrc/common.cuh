@@ -34,6 +34,14 @@ struct ModelSpec {
   double sf2[SBO_MAX_G], sn2[SBO_MAX_G];   // sn2 already includes + eps_f32 (GP_Safe.py:229)
 };
 
+// constants of the fantasy expander (constraint GPs only: entry c is GP c+1)
+struct FantasyConsts {
+  int nc, d, npad;
+  double beta;
+  double sf2[SBO_MAX_G - 1], sn2[SBO_MAX_G - 1];
+  double inv_ell[SBO_MAX_G - 1][SBO_MAX_D];
+};
+
 // numpy.linspace coordinate of axis k at index i: lo + i*step (two roundings, no FMA), last = hi.
 __device__ __forceinline__ double axis_coord(const GridSpec& g, int k, long long i) {
   if (g.pts[k] > 1 && i == g.pts[k] - 1) return g.hi[k];
@@ -114,6 +122,7 @@ struct sbo_ctx {
   DevBuf imp_rows;
   DevBuf vx, vz, aux_x, aux_z;
   DevBuf pp_x, pp_m, pp_v, pp_k, pp_g;   // scratch of the arbitrary-point posterior calls
+  DevBuf tc_row, tc_col, tc_err;          // FP32 row/column records of the tcgen05 fantasy kernel
   // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
   struct EvPair { cudaEvent_t a, b; int phase; };
   std::vector<EvPair> evlog;
@@ -121,7 +130,7 @@ struct sbo_ctx {
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // options
   int64_t opt_posterior_variant = 0;
-  int64_t opt_fantasy_variant = 0;
+  int64_t opt_fantasy_variant = 1;   // 0: BN=128 (4 TMEM slots), 1: BN=256 (2 slots, less operand traffic)
 };
 
 extern thread_local std::string g_sbo_last_error;

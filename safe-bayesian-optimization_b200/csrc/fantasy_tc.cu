@@ -1,7 +1,464 @@
-// fantasy_tc.cu -- TF32 tcgen05/TMEM fantasy-expander GEMM (placeholder until the kernel lands).
+// fantasy_tc.cu -- TF32 tcgen05/TMEM fantasy-expander GEMM for sm_100a (north_star "Expanders" bullet;
+// SURVEY.md section 8 row a12; not in the reference).
+//
+//   for every candidate x (rows, MMA M = 128) and every unsafe z (columns, MMA N = BN) and every constraint GP c:
+//       acc  = v_x . v_z                         tcgen05.mma kind::tf32, FP32 accumulator in TMEM, K = npad
+//       cov  = k_c(z,x) - acc                    SE-ARD kernel recomputed in the epilogue (ex2.approx)
+//       mu'  = m_z + cov * a_x ,  s2' = s_z - cov^2 * b_x     (rank-1 fantasy update, normalised units)
+//       ok  &= mu' >= 0  &&  mu'^2 >= beta^2 * s2'            (<=> mu' - beta*sqrt(max(s2',0)) >= 0)
+//   g(x) = popcount over z of ok  -> atomicAdd per candidate.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0   TMA producer: 3-D tensor maps over Vx[c][row][k] / Vz[c][row][k], 128-byte swizzled boxes of
+//            32 TF32 columns, STAGES-deep smem ring (full/empty mbarriers)
+//   warp 1   MMA issuer: one elected lane issues 4 x (M128,N=BN,K8) tcgen05.mma per stage; tcgen05.commit
+//            releases the smem stage and, after the last K block, publishes the TMEM accumulator slot
+//   warp 2   TMEM allocator (512 columns = 512/BN accumulator slots)
+//   warp 3   column-record loader: per (z tile, constraint) unit one cp.async.bulk of BN records into smem
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 -> registers, fused kernel/rank-1/threshold math, per-row
+//            bitmask AND across constraints, popcount into a per-thread counter.
+// A "unit" is (z tile, constraint); TMEM slots form a ring over units so the epilogue of unit u overlaps the
+// MMAs of unit u+1.  Work items (x tile, chunk of z tiles) are rasterised so that concurrently resident CTAs
+// share z chunks (operand reuse in L2).
 #include "common.cuh"
-struct FantasyConsts;
-int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, long long nx, long long nz, long long nxp, long long nzp,
-                   const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c) {
-  return sbo_fail(ctx, SBO_ERR_INVALID, "TF32 fantasy kernel not built yet");
+#include <cuda.h>
+#include <math.h>
+
+namespace tc {
+
+constexpr int BM = 128;        // candidates per tile (MMA M, TMEM lanes)
+constexpr int BK = 32;         // TF32 elements per smem row = 128 bytes = one SWIZZLE_128B atom
+constexpr int UK = 8;          // K per tcgen05.mma kind::tf32
+constexpr int GX = 37;         // x tiles per raster group (4 z chunks in flight on 148 SMs)
+
+struct Params {
+  int nc, kblocks, nkb, npad, split, nxt, nzt, zt_per_chunk, nzc;   // kblocks = split ? 3*nkb : nkb
+  long long nx, nz, nxp, nzp, n_items;
+  const float* rowrec;   // [nc][nxp][RS]
+  const float* colrec;   // [nc][nzp][RS]
+  int* counts;           // [nx]
+  int* err;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      if (err) atomicExch(err, tag);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// work item -> (x tile, z chunk); groups of GX x tiles sweep all z chunks before the next group starts
+__device__ __forceinline__ bool item_coords(const Params& p, long long item, int& xt, int& zc) {
+  const long long per_group = (long long)GX * p.nzc;
+  const int xg = (int)(item / per_group);
+  const int r = (int)(item % per_group);
+  zc = r / GX;
+  xt = xg * GX + r % GX;
+  return xt < p.nxt;
+}
+
+template <int BN, int D4>
+struct Cfg {
+  static constexpr int RS = 4 * D4 + 4;                 // floats per row/column record
+  static constexpr int SLOTS = 512 / BN;                // TMEM accumulator slots
+  static constexpr int STAGE_BYTES = (BM + BN) * 128;   // A tile + B tile
+  static constexpr int STAGES = (BN == 128) ? 5 : 4;
+  static constexpr int COL_BYTES = BN * RS * 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * COL_BYTES + 256;
+};
+
+template <int BN, int D4>
+__global__ void __launch_bounds__(256, 1)
+k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN, D4>;
+  constexpr int RS = C::RS, SLOTS = C::SLOTS, STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t tiles = base;
+  const uint32_t colbuf = base + STAGES * C::STAGE_BYTES;
+  const float* colbuf_ptr = reinterpret_cast<const float*>(base_ptr + STAGES * C::STAGE_BYTES);
+  const uint32_t bars = colbuf + 2 * C::COL_BYTES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(base_ptr + STAGES * C::STAGE_BYTES + 2 * C::COL_BYTES + 200);
+  // barrier map (8 bytes each)
+  auto bar_full = [&](int s) { return bars + 8 * s; };
+  auto bar_empty = [&](int s) { return bars + 8 * (STAGES + s); };
+  auto bar_tfull = [&](int s) { return bars + 8 * (2 * STAGES + s); };
+  auto bar_tempty = [&](int s) { return bars + 8 * (2 * STAGES + SLOTS + s); };
+  auto bar_cfull = [&](int b) { return bars + 8 * (2 * STAGES + 2 * SLOTS + b); };
+  auto bar_cempty = [&](int b) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 2 + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull(b), 1); mbar_init(bar_cempty(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int xt, zc;
+        if (!item_coords(p, item, xt, zc)) continue;
+        const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
+        for (int zt = zt0; zt < zt1; ++zt)
+          for (int c = 0; c < p.nc; ++c)
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(bar_empty(stage), phase ^ 1, p.err, 1);
+              mbar_expect_tx(bar_full(stage), C::STAGE_BYTES);
+              const uint32_t sa = tiles + stage * C::STAGE_BYTES;
+              // split-TF32 rows are [hi | lo]: K segments (x_hi,z_hi), (x_hi,z_lo), (x_lo,z_hi)
+              const int seg = kb / p.nkb, kk = (kb - seg * p.nkb) * BK;
+              tma_load_3d(sa, &tmA, bar_full(stage), kk + (seg == 2 ? p.npad : 0), xt * BM, c);
+              tma_load_3d(sa + BM * 128, &tmB, bar_full(stage), kk + (seg == 1 ? p.npad : 0), zt * BN, c);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int slot = 0; uint32_t sphase = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int xt, zc;
+        if (!item_coords(p, item, xt, zc)) continue;
+        const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
+        for (int zt = zt0; zt < zt1; ++zt)
+          for (int c = 0; c < p.nc; ++c) {
+            mbar_wait(bar_tempty(slot), sphase ^ 1, p.err, 2);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(slot * BN);
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(bar_full(stage), phase, p.err, 3);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t sa = tiles + stage * C::STAGE_BYTES;
+              const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + BM * 128);
+#pragma unroll
+              for (int k = 0; k < BK / UK; ++k)
+                mma_tf32(tmem_d, adesc + (uint64_t)(k * UK * 4 / 16), bdesc + (uint64_t)(k * UK * 4 / 16), idesc,
+                         (kb | k) ? 1u : 0u);
+              mma_commit(bar_empty(stage));                 // frees the smem stage when these MMAs retire
+              if (kb == p.kblocks - 1) mma_commit(bar_tfull(slot));   // accumulator complete
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ column-record loader ================================
+    if (lane == 0) {
+      int b = 0; uint32_t bphase = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int xt, zc;
+        if (!item_coords(p, item, xt, zc)) continue;
+        const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
+        for (int zt = zt0; zt < zt1; ++zt)
+          for (int c = 0; c < p.nc; ++c) {
+            mbar_wait(bar_cempty(b), bphase ^ 1, p.err, 4);
+            mbar_expect_tx(bar_cfull(b), C::COL_BYTES);
+            bulk_load_1d(colbuf + b * C::COL_BYTES, p.colrec + ((size_t)c * p.nzp + (size_t)zt * BN) * RS, C::COL_BYTES,
+                         bar_cfull(b));
+            if (++b == 2) { b = 0; bphase ^= 1; }
+          }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int q = warp - 4;                       // TMEM lane quarter: this warp may touch lanes 32q .. 32q+31
+    const int row = q * 32 + lane;
+    int slot = 0; uint32_t sphase = 0;
+    int b = 0; uint32_t bphase = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int xt, zc;
+      if (!item_coords(p, item, xt, zc)) continue;
+      const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
+      const long long xrow = (long long)xt * BM + row;
+      int cnt = 0;
+      for (int zt = zt0; zt < zt1; ++zt) {
+        uint32_t bits[BN / 32];
+#pragma unroll
+        for (int h = 0; h < BN / 32; ++h) bits[h] = 0xffffffffu;
+        for (int c = 0; c < p.nc; ++c) {
+          // row record of this candidate for constraint c: xx[4*D4], Cx, a, b', pad
+          float xx[4 * D4];
+          const float4* rr = reinterpret_cast<const float4*>(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
+#pragma unroll
+          for (int v = 0; v < D4; ++v) {
+            const float4 t = __ldg(rr + v);
+            xx[4 * v] = t.x; xx[4 * v + 1] = t.y; xx[4 * v + 2] = t.z; xx[4 * v + 3] = t.w;
+          }
+          const float4 rt = __ldg(rr + D4);
+          const float Cx = rt.x, ax = rt.y, bx = rt.z;
+          mbar_wait(bar_cfull(b), bphase, p.err, 5);
+          mbar_wait(bar_tfull(slot), sphase, p.err, 6);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
+#pragma unroll
+          for (int h = 0; h < BN / 32; ++h) {
+            uint32_t r[32];
+            tmem_ld32(taddr + h * 32, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float4* rec = cb + (size_t)(h * 32 + j) * (RS / 4);
+              const float4 tail = rec[D4];                     // Bz, m_z, s'_z, pad
+              float e = Cx - tail.x;
+#pragma unroll
+              for (int v = 0; v < D4; ++v) {
+                const float4 zc4 = rec[v];
+                e = fmaf(xx[4 * v], zc4.x, e); e = fmaf(xx[4 * v + 1], zc4.y, e);
+                e = fmaf(xx[4 * v + 2], zc4.z, e); e = fmaf(xx[4 * v + 3], zc4.w, e);
+              }
+              const float cov = ex2_approx(e) - __uint_as_float(r[j]);
+              const float mu = fmaf(cov, ax, tail.y);
+              const float t = fmaf(-(cov * cov), bx, tail.z);
+              const bool ok = (mu >= 0.f) && (mu * mu >= t);
+              w |= ok ? (1u << j) : 0u;
+            }
+            bits[h] &= w;
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(bar_tempty(slot)); mbar_arrive(bar_cempty(b)); }
+          if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+          if (++b == 2) { b = 0; bphase ^= 1; }
+        }
+#pragma unroll
+        for (int h = 0; h < BN / 32; ++h) cnt += __popc(bits[h]);
+      }
+      if (xrow < p.nx && cnt) atomicAdd(p.counts + xrow, cnt);
+    }
+  }
+  // ---- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 record builders.  h = log2(e)/2 so that  k_c(z,x) = exp2(Cx - Bz + sum_k xx_k z_k)
+//   row (candidate x):  xx_k = 2 h w_ck x_k ; Cx = log2 sf2_c - h sum_k w_ck x_k^2 ; a = beta*sigma/(sigma^2+sn2) ;
+//                       b' = beta^2/(sigma^2+sn2)
+//   col (unsafe z):     z_k ; Bz = h sum_k w_ck z_k^2 ; m_z = mean/Ystd ; s'_z = beta^2 var/Ystd^2
+// ---------------------------------------------------------------------------------------------
+template <int D4>
+__global__ void __launch_bounds__(256)
+k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, const double* __restrict__ coords,
+             const double* __restrict__ a, const double* __restrict__ b, float* __restrict__ rec) {
+  constexpr int RS = 4 * D4 + 4;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (t >= npadrows) return;
+  float* o = rec + ((size_t)c * npadrows + t) * RS;
+  if (t >= n) {
+    for (int k = 0; k < RS; ++k) o[k] = 0.f;
+    if (!is_row) o[4 * D4 + 1] = -1e30f;         // padded z columns can never become safe
+    return;
+  }
+  const double h = 0.5 * 1.4426950408889634;
+  double q = 0.0;
+  for (int k = 0; k < 4 * D4; ++k) {
+    const double x = (k < fc.d) ? coords[(size_t)k * n + t] : 0.0;
+    const double w = (k < fc.d) ? fc.inv_ell[c][k] : 0.0;
+    q += w * x * x;
+    o[k] = is_row ? (float)(2.0 * h * w * x) : (float)x;
+  }
+  const double av = a[(size_t)c * n + t], bv = b[(size_t)c * n + t];
+  if (is_row) {
+    o[4 * D4] = (float)(log2(fc.sf2[c]) - h * q);
+    o[4 * D4 + 1] = (float)av;
+    o[4 * D4 + 2] = (float)(fc.beta * fc.beta * bv);
+  } else {
+    o[4 * D4] = (float)(h * q);
+    o[4 * D4 + 1] = (float)av;
+    o[4 * D4 + 2] = (float)(fc.beta * fc.beta * bv);
+  }
+  o[4 * D4 + 3] = 0.f;
+}
+
+static int make_map(sbo_ctx* ctx, CUtensorMap* map, const float* base, int rowlen, long long rows, int nc, int box_rows) {
+  cuuint64_t gdim[3] = {(cuuint64_t)rowlen, (cuuint64_t)rows, (cuuint64_t)nc};
+  cuuint64_t gstr[2] = {(cuuint64_t)rowlen * 4, (cuuint64_t)rows * rowlen * 4};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    const char* s = nullptr;
+    cuGetErrorString(r, &s);
+    return sbo_fail(ctx, SBO_ERR_CUDA, std::string("cuTensorMapEncodeTiled: ") + (s ? s : "?"));
+  }
+  return SBO_OK;
+}
+
+template <int BN, int D4>
+static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
+                  const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err) {
+  using C = Cfg<BN, D4>;
+  CUtensorMap tmA, tmB;
+  const int rowlen = split ? 2 * fc.npad : fc.npad;
+  SBO_TRY(make_map(ctx, &tmA, Vx, rowlen, nxp, fc.nc, BM));
+  SBO_TRY(make_map(ctx, &tmB, Vz, rowlen, nzp, fc.nc, BN));
+  Params p{};
+  p.nc = fc.nc; p.nkb = fc.npad / BK; p.kblocks = split ? 3 * p.nkb : p.nkb; p.npad = fc.npad; p.split = split;
+  p.nx = nx; p.nz = nz; p.nxp = nxp; p.nzp = nzp;
+  p.nxt = (int)cdiv(nx, BM); p.nzt = (int)cdiv(nz, BN);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  // chunk the z tiles so that there are >= ~8 items per SM, each item >= 4 z tiles when possible
+  int ztc = 32;
+  while (ztc > 4 && (long long)p.nxt * cdiv(p.nzt, ztc) < 8LL * sms) ztc /= 2;
+  p.zt_per_chunk = ztc;
+  p.nzc = (int)cdiv(p.nzt, ztc);
+  p.n_items = cdiv(p.nxt, GX) * GX * (long long)p.nzc;
+  p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc<BN, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = (int)((p.n_items < sms) ? p.n_items : sms);
+  k_fantasy_tc<BN, D4><<<grid, 256, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
+}  // namespace tc
+
+int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
+                   long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c) {
+  const int d = fc.d, nc = fc.nc;
+  const int D4 = d <= 4 ? 1 : 2;
+  const int RS = 4 * D4 + 4;
+  SBO_REQUIRE(fc.npad % tc::BK == 0, "npad must be a multiple of 32");
+  SBO_REQUIRE(nxp % 256 == 0 && nzp % 256 == 0, "padded row counts must be multiples of 256");
+  SBO_TRY(sbo_ensure(ctx, ctx->tc_row, sizeof(float) * (size_t)nc * nxp * RS));
+  SBO_TRY(sbo_ensure(ctx, ctx->tc_col, sizeof(float) * (size_t)nc * nzp * RS));
+  SBO_TRY(sbo_ensure(ctx, ctx->tc_err, sizeof(int)));
+  SBO_CUDA(cudaMemsetAsync(ctx->tc_err.p, 0, sizeof(int), ctx->stream));
+  const double* xn = aux_x; const double* ax = xn + (size_t)d * nx; const double* bx = ax + (size_t)nc * nx;
+  const double* zn = aux_z; const double* mz = zn + (size_t)d * nz; const double* sz = mz + (size_t)nc * nz;
+  float* rowrec = (float*)ctx->tc_row.p;
+  float* colrec = (float*)ctx->tc_col.p;
+  ev_begin(ctx, 6);
+  if (D4 == 1) {
+    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec);
+    SBO_LAUNCH_CHECK();
+    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec);
+    SBO_LAUNCH_CHECK();
+  } else {
+    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec);
+    SBO_LAUNCH_CHECK();
+    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec);
+    SBO_LAUNCH_CHECK();
+  }
+  int* err = (int*)ctx->tc_err.p;
+  const bool wide = ctx->opt_fantasy_variant == 1;
+  ev_end(ctx);            // record prep = phase 6
+  ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)
+  if (D4 == 1) {
+    if (wide) SBO_TRY((tc::launch<256, 1>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
+    else SBO_TRY((tc::launch<128, 1>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
+  } else {
+    if (wide) SBO_TRY((tc::launch<256, 2>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
+    else SBO_TRY((tc::launch<128, 2>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
+  }
+  return SBO_OK;
 }

@@ -304,13 +304,6 @@ int pairs_lipschitz(sbo_ctx* ctx, bool goose, double beta, const double* L, sbo_
 // =============================================================================================
 // Fantasy mode, FP64 SIMT reference kernel
 // =============================================================================================
-struct FantasyConsts {
-  int nc, d, npad;
-  double beta;
-  double sf2[SBO_MAX_G - 1], sn2[SBO_MAX_G - 1];
-  double inv_ell[SBO_MAX_G - 1][SBO_MAX_D];
-};
-
 // gather V rows of the compacted points: Vout[c][t][0..npad) = vall[c][idx[t]][0..npad)  (zero rows for padding)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -465,20 +458,21 @@ k_counts_scatter(long long nx, const long long* __restrict__ idx, const int* __r
   if (c > 0) atomicOr(mask + (p >> 5), 1u << (p & 31));
 }
 
-int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, long long nx, long long nz, long long nxp, long long nzp,
-                   const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c);
+int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
+                   long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c);
 
 int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host) {
   SBO_REQUIRE(ctx->have_sets, "fantasy expander needs the sets (call sbo_sets)");
   SBO_REQUIRE(out != nullptr, "null result");
-  SBO_REQUIRE(precision == SBO_PREC_FP64 || precision == SBO_PREC_TF32, "bad precision");
+  SBO_REQUIRE(precision == SBO_PREC_FP64 || precision == SBO_PREC_TF32 || precision == SBO_PREC_TF32X3, "bad precision");
   const ModelSpec& ms = ctx->ms;
   const GridSpec& gs = ctx->gs;
   const int nc = ms.G - 1, d = gs.d, np = ms.npad;
   const long long count = gs.count, nw = mask_words(ctx);
   SBO_REQUIRE(nc >= 1, "fantasy expander needs at least one constraint GP");
-  SBO_REQUIRE(ctx->keep_v == (precision == SBO_PREC_FP64 ? 1 : 2),
-              "fantasy expander: run sbo_posterior with keep_v = 1 (FP64) or 2 (TF32) first");
+  SBO_REQUIRE(ctx->keep_v == (precision == SBO_PREC_FP64 ? 1 : (precision == SBO_PREC_TF32 ? 2 : 3)),
+              "fantasy expander: run sbo_posterior with keep_v = 1 (FP64), 2 (TF32) or 3 (TF32x3) first");
+  const int rowlen = (precision == SBO_PREC_TF32X3) ? 2 * np : np;   // split rows are [hi | lo]
   memset(out, 0, sizeof(*out));
   out->best_idx = -1; out->best_value = -INFINITY;
   for (int c = 0; c < SBO_MAX_G; ++c) { out->per_idx[c] = -1; out->per_value[c] = -INFINITY; }
@@ -505,10 +499,10 @@ int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out
     if (counts_host) memset(counts_host, 0, sizeof(int32_t) * (size_t)count);
     return SBO_OK;
   }
-  const long long nxp = cdiv(nx, 128) * 128, nzp = cdiv(nz, 128) * 128;
+  const long long nxp = cdiv(nx, 256) * 256, nzp = cdiv(nz, 256) * 256;
   const size_t esz = precision == SBO_PREC_FP64 ? sizeof(double) : sizeof(float);
-  SBO_TRY(sbo_ensure(ctx, ctx->vx, esz * (size_t)nc * nxp * np));
-  SBO_TRY(sbo_ensure(ctx, ctx->vz, esz * (size_t)nc * nzp * np));
+  SBO_TRY(sbo_ensure(ctx, ctx->vx, esz * (size_t)nc * nxp * rowlen));
+  SBO_TRY(sbo_ensure(ctx, ctx->vz, esz * (size_t)nc * nzp * rowlen));
   SBO_TRY(sbo_ensure(ctx, ctx->aux_x, sizeof(double) * (size_t)nx * (d + 2 * nc)));
   SBO_TRY(sbo_ensure(ctx, ctx->aux_z, sizeof(double) * (size_t)nz * (d + 2 * nc)));
   const long long* xi = (const long long*)ctx->xs_idx.p;
@@ -519,9 +513,9 @@ int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out
     k_gather_rows<double><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, np, nz, nzp, count, zi, (const double*)ctx->vall.p, (double*)ctx->vz.p);
     SBO_LAUNCH_CHECK();
   } else {
-    k_gather_rows<float><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, np, nx, nxp, count, xi, (const float*)ctx->vall.p, (float*)ctx->vx.p);
+    k_gather_rows<float><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nx, nxp, count, xi, (const float*)ctx->vall.p, (float*)ctx->vx.p);
     SBO_LAUNCH_CHECK();
-    k_gather_rows<float><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, np, nz, nzp, count, zi, (const float*)ctx->vall.p, (float*)ctx->vz.p);
+    k_gather_rows<float><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nz, nzp, count, zi, (const float*)ctx->vall.p, (float*)ctx->vz.p);
     SBO_LAUNCH_CHECK();
   }
   double* xn = (double*)ctx->aux_x.p; double* ax = xn + (size_t)d * nx; double* bx = ax + (size_t)nc * nx;
@@ -533,8 +527,8 @@ int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out
   ev_end(ctx);
   int* cnt_c = (int*)ctx->counts.p;            // per compacted candidate
   int* cnt_pt = cnt_c + count;                 // per local point
-  ev_begin(ctx, 4);
   if (precision == SBO_PREC_FP64) {
+    ev_begin(ctx, 4);
     dim3 grid((unsigned)cdiv(nz, FB), (unsigned)cdiv(nx, FB));
     SBO_REQUIRE(grid.y <= 65535, "too many candidates for the FP64 fantasy kernel");
 #define FL(DD) k_fantasy_f64<DD><<<grid, 256, 0, ctx->stream>>>(fc, nx, nz, nxp, nzp, (const double*)ctx->vx.p, (const double*)ctx->vz.p, xn, ax, bx, zn, mz, sz, cnt_c)
@@ -542,8 +536,8 @@ int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out
                  case 5: FL(5); break; case 6: FL(6); break; case 7: FL(7); break; default: FL(8); break; }
 #undef FL
     SBO_LAUNCH_CHECK();
-  } else {
-    SBO_TRY(fantasy_tc_run(ctx, fc, nx, nz, nxp, nzp, (const float*)ctx->vx.p, (const float*)ctx->vz.p,
+  } else {   // record prep is logged as phase 6, the GEMM kernel as phase 4 (begun inside)
+    SBO_TRY(fantasy_tc_run(ctx, fc, precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p, (const float*)ctx->vz.p,
                            (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt_c));
   }
   ev_end(ctx);

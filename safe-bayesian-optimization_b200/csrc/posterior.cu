@@ -111,7 +111,7 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
 #define PB_BP 64
 #define PB_BK 16
 
-template <int EMIT>   // 0 none, 1 fp64, 2 fp32(tf32-rounded)
+template <int EMIT>   // 0 none, 1 fp64, 2 fp32 (tf32-rounded), 3 split tf32 pair [hi | lo] (row length 2*npad)
 __global__ void __launch_bounds__(256)
 k_solve_var(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, int valid,
             double* __restrict__ var_out, long long out_ld, void* __restrict__ vall, long long v_count) {
@@ -166,8 +166,18 @@ k_solve_var(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, in
       for (int j = 0; j < 4; ++j) {
         const long long pl = (long long)blockIdx.x * PB_BP + tx * 4 + j;
         if (pl < valid) {
-          const size_t row = ((size_t)(g - 1) * v_count + p0 + pl) * np + rb * PB_BM + ty * 4;
-          if (EMIT == 1) {
+          const size_t row = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * PB_BM + ty * 4;
+          if (EMIT == 3) {
+            float* o = reinterpret_cast<float*>(vall) + row;
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              hi[i] = to_tf32((float)acc[i][j]);
+              lo[i] = to_tf32((float)(acc[i][j] - (double)hi[i]));
+            }
+            *reinterpret_cast<float4*>(o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(o + np) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          } else if (EMIT == 1) {
             double* o = reinterpret_cast<double*>(vall) + row;
             *reinterpret_cast<double2*>(o) = make_double2(acc[0][j], acc[1][j]);
             *reinterpret_cast<double2*>(o + 2) = make_double2(acc[2][j], acc[3][j]);
@@ -229,6 +239,8 @@ static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, i
     k_solve_var<1><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
   else if (keep_v == 2)
     k_solve_var<2><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+  else if (keep_v == 3)
+    k_solve_var<3><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
   else
     k_solve_var<0><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
   SBO_LAUNCH_CHECK();
@@ -249,7 +261,7 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   SBO_REQUIRE(ctx->have_model, "sbo_posterior: no model (call sbo_set_model)");
   SBO_REQUIRE(ctx->have_grid, "sbo_posterior: no grid (call sbo_set_grid / sbo_set_points)");
   SBO_REQUIRE(ctx->gs.d == ctx->ms.d, "grid and model dimensions differ");
-  SBO_REQUIRE(keep_v >= 0 && keep_v <= 2, "keep_v must be 0, 1 or 2");
+  SBO_REQUIRE(keep_v >= 0 && keep_v <= 3, "keep_v must be 0, 1, 2 or 3");
   const ModelSpec& ms = ctx->ms;
   const long long count = ctx->gs.count;
   SBO_REQUIRE(count > 0, "empty shard");
@@ -260,7 +272,7 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   SBO_TRY(sbo_ensure(ctx, ctx->kx, sizeof(double) * (size_t)ms.G * ms.npad * P));
   ctx->keep_v = 0;
   if (keep_v && ms.G > 1) {
-    const size_t esz = keep_v == 1 ? sizeof(double) : sizeof(float);
+    const size_t esz = keep_v == 1 ? sizeof(double) : (keep_v == 3 ? 2 * sizeof(float) : sizeof(float));
     SBO_TRY(sbo_ensure(ctx, ctx->vall, esz * (size_t)(ms.G - 1) * count * ms.npad));
   }
   SBO_CUDA(cudaMemsetAsync(ctx->lmax.p, 0, sizeof(double) * SBO_MAX_G, ctx->stream));

@@ -43,6 +43,10 @@ class GridEngine:
         self.grid_kind = None
         if stream is not None:
             self._ck(self._lib.sbo_set_stream(self._h, C.c_void_p(int(stream))))
+        import os
+        for env, opt in (("SBO_FANTASY_VARIANT", "fantasy_variant"), ("SBO_POSTERIOR_VARIANT", "posterior_variant")):
+            if os.environ.get(env):
+                self.set_option(opt, int(os.environ[env]))
 
     # -- plumbing ---------------------------------------------------------------------------
     def _ck(self, rc):
@@ -254,8 +258,8 @@ class GridEngine:
         if upload:
             self.set_model(ds)
         fantasy = mode == "fantasy"
-        prec = capi.PREC_TF32 if precision == "tf32" else capi.PREC_FP64
-        keep_v = 0 if not fantasy else (2 if prec == capi.PREC_TF32 else 1)
+        prec, kv = capi.PRECISIONS[precision]
+        keep_v = kv if fantasy else 0
         self.posterior(with_grad=not fantasy and L is None, keep_v=keep_v, fetch=False)
         s = self.sets(beta, unsafe_rule)
         out = dict(s)

@@ -9,7 +9,7 @@ expander pair kernel -> deterministic arg-reductions (lowest grid index on ties)
 Additive keyword arguments (defaults reproduce the reference's semantics):
   grid_points_per_dim  400 for d <= 2 (the reference's plot grid, test/test_SafeOpt.py:325-326)
   expander_mode        'lipschitz' (reference-exact pair test) | 'fantasy' (north_star GEMM expander)
-  precision            'fp64' | 'tf32' (fantasy GEMM only)
+  precision            'fp64' | 'tf32' | 'tf32x3' (fantasy GEMM only)
   unsafe_rule          'all' (reference: lcb_constraint_min returns the MAX, SafeOpt.py:73-77) | 'any'
 """
 from __future__ import annotations
@@ -64,7 +64,7 @@ class BO(GP):
         if self._step is None:
             capi = self._capi()
             fantasy = self.expander_mode == 'fantasy'
-            keep_v = 0 if not fantasy else (2 if self.precision == 'tf32' else 1)
+            keep_v = capi.PRECISIONS[self.precision][1] if fantasy else 0
             self.engine.posterior(with_grad=True, keep_v=keep_v, fetch=False)
             rule = capi.UNSAFE_ALL if self.unsafe_rule == 'all' else capi.UNSAFE_ANY
             self._step = {"sets": self.engine.sets(self.b, rule), "L": self.engine.lipschitz()}
@@ -142,7 +142,7 @@ class BO(GP):
         capi = self._capi()
         if "expander" not in st:
             if self.expander_mode == 'fantasy':
-                prec = capi.PREC_TF32 if self.precision == 'tf32' else capi.PREC_FP64
+                prec = capi.PRECISIONS[self.precision][0]
                 st["expander"] = self.engine.expander(self.b, None, capi.MODE_FANTASY, prec)
             else:
                 L = np.full(self.n_fun, st["L"][self.n_fun - 1])   # SafeOpt.py:110: leaked i = n_fun-1

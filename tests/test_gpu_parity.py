@@ -429,3 +429,88 @@ def test_c4_full_size_properties(engine, oracle):
     Yraw = ds["Y_norm"] * ds["Y_std"] + ds["Y_mean"]
     mt, vt = engine.point_posterior(Xraw)
     assert np.max(np.abs(mt - Yraw) / ds["Y_std"]) < 0.2 and np.max(vt / ds["Y_std"] ** 2) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# fantasy expander, TF32 tcgen05/TMEM kernel.  Three checks, tolerances stated on the FP64 margin
+#   m(z,x) = min_i (mu'_i - beta*sigma'_i)   (normalised units)  of a (z,x) pair:
+#   (1) implementation: vs the oracle evaluated with the SAME TF32-rounded operands (exact products, wide
+#       accumulation, FP64 epilogue).  Only FP32 accumulation order / FP32 epilogue rounding may differ:
+#       decisions may differ where |m| <= IMPL_TOL * sf2 * (1 + gain(x)).
+#   (2) TF32 mode vs FP64: operand rounding (2^-11 relative) perturbs v_x.v_z by up to ~1e-3*sf2 and the rank-1
+#       update multiplies that by gain(x) = beta*sigma(x)/(sigma^2(x)+sn2): decisions may differ where
+#       |m| <= TF32_TOL * sf2 * (1 + gain(x)).  (For ill-conditioned fits, sn2 ~ 5e-5, gain reaches ~200 and the
+#       single-pass TF32 mode is not usable -- that is what TF32X3 is for.)
+#   (3) TF32X3 mode (split operands, three passes) vs FP64: |m| <= IMPL_TOL * sf2 * (1 + gain(x)).
+# ------------------------------------------------------------------------------------------------
+TF32_TOL = 1e-3
+IMPL_TOL = 2e-5
+
+
+def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, precision):
+    capi = _capi()
+    prec, keep_v = capi.PRECISIONS[precision]
+    engine.set_option("fantasy_variant", variant)
+    engine.set_model(ds)
+    engine.set_grid(lo, hi, grid)
+    m, v = engine.posterior(keep_v=keep_v)
+    engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
+    ex = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+    engine.set_option("fantasy_variant", 1)
+    pts = oracle.make_grid(lo, hi, grid)
+    lcb, _ = oracle.bounds(m, v, beta)
+    S, Z = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, rule)
+    got = ex["counts"][S].astype(np.int64)
+    assert (ex["counts"][~S] == 0).all()
+    assert ex["n_x"] == S.sum() and ex["n_z"] == Z.sum()
+    margin = np.abs(oracle.fantasy_margin(pts, ds, beta, S, Z))            # (|Z|,|S|)
+    G, d = m.shape[1], pts.shape[1]
+    gain = np.zeros(S.sum())
+    sf2max = 0.0
+    for i in range(1, G):
+        _, sf2, sn2 = oracle.unpack_hyper(ds["hypopt"][:, i], d)
+        sf2max = max(sf2max, sf2)
+        vn = v[S, i] / ds["Y_std"][i] ** 2
+        gain = np.maximum(gain, beta * np.sqrt(vn) / (vn + sn2 + oracle.EPS_F32))
+    scale = sf2max * (1.0 + gain)[None, :]
+    w64 = oracle.fantasy_counts(pts, ds, beta, S, Z)[S]
+    out = {"newly_safe_fp64": int(w64.sum())}
+    if precision == "tf32":
+        wtf = oracle.fantasy_counts(pts, ds, beta, S, Z, dtype="tf32")[S]
+        amb_impl = (margin <= IMPL_TOL * scale).sum(axis=0)
+        d1 = np.abs(got - wtf)
+        # the TF32-operand oracle decides on ITS margin; allow its own near-threshold pairs as well
+        assert np.all(d1 <= amb_impl + (np.abs(wtf - w64) > 0) * 2 + 2), (int(d1.max()), int(amb_impl.max()))
+        amb = (margin <= TF32_TOL * scale).sum(axis=0)
+        d2 = np.abs(got - w64)
+        assert np.all(d2 <= amb), (int(d2.max()), int(amb.max()), int((d2 > amb).sum()))
+        out.update(diff_vs_tf32_oracle=int(d1.sum()), diff_vs_fp64=int(d2.sum()), ambiguous=int(amb.sum()))
+    else:
+        amb = (margin <= IMPL_TOL * scale).sum(axis=0)
+        d2 = np.abs(got - w64)
+        assert np.all(d2 <= amb), (int(d2.max()), int(amb.max()), int((d2 > amb).sum()))
+        out.update(diff_vs_fp64=int(d2.sum()), ambiguous=int(amb.sum()))
+    return out
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name,n,beta,grid,rule", [("c1", 9, 3.0, [48, 40], "all"), ("c3", 20, 2.0, [45, 61], "any"),
+                                                    ("c3", 35, 2.0, [70, 50], "all")])
+def test_fantasy_tensor_core_counts(engine, oracle, request, name, n, beta, grid, rule, variant, precision):
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    r = _fantasy_tc_case(engine, oracle, ds, gold["lo"], gold["hi"], grid, beta, rule, variant, precision)
+    print(f"fantasy {precision} v{variant} {name} n={n}: {r}")
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fantasy_tensor_core_synthetic(engine, oracle, variant, precision):
+    from sbo_b200 import workloads
+    for (d, ppd, n, G) in [(3, 14, 70, 3), (4, 9, 200, 4), (6, 5, 130, 3)]:
+        ds, lo, hi, pts_per_dim, beta = workloads.small(d=d, pts_per_dim=ppd, n=n, seed=7 + d, G=G)
+        r = _fantasy_tc_case(engine, oracle, dict(ds), lo, hi, pts_per_dim, beta, "any", variant, precision)
+        print(f"fantasy {precision} v{variant} synthetic d={d} n={n}: {r}")
+        if precision == "tf32x3":
+            assert r["diff_vs_fp64"] <= max(2, r["newly_safe_fp64"] // 1000)
