@@ -89,6 +89,10 @@ int sbo_get_model(sbo_ctx* ctx, double* L, double* W, double* alpha);
 int sbo_set_grid(sbo_ctx* ctx, int d, const int64_t* pts_per_dim, const double* lo, const double* hi);
 int sbo_set_points(sbo_ctx* ctx, int64_t N, int d, const double* pts);
 int sbo_set_shard(sbo_ctx* ctx, int64_t first, int64_t count);
+/* block-cyclic ownership (multi-GPU): rank r owns the blocks b = r, r+nranks, ... of `block` consecutive
+ * grid points (block a multiple of 32), which balances |S| and |Z| across ranks.  Local point p maps to the
+ * global index ((p / block) * nranks + rank) * block + p % block; *count = number of local points. */
+int sbo_set_shard_cyclic(sbo_ctx* ctx, int rank, int nranks, int64_t block, int64_t* count);
 int sbo_point_coords(sbo_ctx* ctx, int64_t global_idx, double* x /* d */);
 
 /* ---- posterior:  GP.GP_inference vmapped over the grid  (GP_Safe.py:310-352) -------------
@@ -151,6 +155,25 @@ typedef struct sbo_pair_result {
 int sbo_expander(sbo_ctx* ctx, int mode, int precision, double beta, const double* L /* G, lipschitz mode */,
                  sbo_pair_result* out, int32_t* counts /* count, fantasy mode, or NULL */);
 int sbo_goose_target(sbo_ctx* ctx, double beta, const double* L /* G */, sbo_pair_result* out);
+/* ---- the same pair stage in five steps, for a grid sharded over ranks ---------------
+ * Every rank pairs ALL candidates x in S (gathered from all ranks) with ITS OWN unsafe points z:
+ *   sbo_pairs_prepare     compact the local S and Z, build the local z-side operands
+ *   sbo_pairs_export_dev  write the local candidates' rows [coords d | ucb G-1 | xn d | a G-1 | b G-1] (doubles,
+ *                         row_doubles per candidate) and, in fantasy mode, their V rows (vrow_bytes per
+ *                         candidate) into caller-owned DEVICE buffers  -> all-gather them (NCCL)
+ *   sbo_pairs_import_dev  hand the concatenation of all ranks' rows back (n_total candidates)
+ *   sbo_pairs_run_dev     result_dev: lipschitz uint8[(G-1)*n_total] hit flags | fantasy int32[n_total] counts
+ *                         (goose: uint8[(G-1)*n_z_local], no exchange needed) -> all-reduce max / sum (NCCL)
+ *   sbo_pairs_finish_dev  masks + arg-reductions on the local shard; the local candidates are rows
+ *                         [offset, offset + n_x_local) of the reduced result.  `out` holds LOCAL optima with
+ *                         GLOBAL indices; the caller reduces them across ranks (value, then lowest index).
+ * sbo_expander / sbo_goose_target are these five steps on one GPU. */
+typedef struct sbo_pairs_info { int64_t n_x_local, n_z_local, row_doubles, vrow_bytes; } sbo_pairs_info;
+int sbo_pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const double* L /* G or NULL */, sbo_pairs_info* info);
+int sbo_pairs_export_dev(sbo_ctx* ctx, void* rows_dev, void* vrows_dev);
+int sbo_pairs_import_dev(sbo_ctx* ctx, int64_t n_total, const void* rows_dev, const void* vrows_dev);
+int sbo_pairs_run_dev(sbo_ctx* ctx, int goose, void* result_dev);
+int sbo_pairs_finish_dev(sbo_ctx* ctx, int goose, int64_t offset, const void* result_dev, sbo_pair_result* out, int32_t* counts);
 /* which = idx-1 (lipschitz/target: one mask per constraint) ; fantasy: which = 0 */
 #define SBO_MASK_EXPANDER 4
 #define SBO_MASK_TARGET   5

@@ -37,6 +37,10 @@ class PairResult(C.Structure):
                 ("pairs_algorithmic", C.c_int64), ("pairs_evaluated", C.c_int64), ("n_hit", C.c_int64)]
 
 
+class PairsInfo(C.Structure):
+    _fields_ = [("n_x_local", C.c_int64), ("n_z_local", C.c_int64), ("row_doubles", C.c_int64), ("vrow_bytes", C.c_int64)]
+
+
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 _I64 = C.POINTER(C.c_int64)
@@ -69,6 +73,12 @@ SIGNATURES = {
     "sbo_argreduce": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, _I64, _D]),
     "sbo_expander": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, C.POINTER(PairResult), C.POINTER(C.c_int32)]),
     "sbo_goose_target": (C.c_int, [_P, C.c_double, _D, C.POINTER(PairResult)]),
+    "sbo_set_shard_cyclic": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _I64]),
+    "sbo_pairs_prepare": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, C.POINTER(PairsInfo)]),
+    "sbo_pairs_export_dev": (C.c_int, [_P, _P, _P]),
+    "sbo_pairs_import_dev": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "sbo_pairs_run_dev": (C.c_int, [_P, C.c_int, _P]),
+    "sbo_pairs_finish_dev": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.POINTER(PairResult), C.POINTER(C.c_int32)]),
     "sbo_kernel_launches": (C.c_int64, [_P, C.c_int]),
     "sbo_phase_ms": (C.c_int, [_P, C.c_int, _D]),
     "sbo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

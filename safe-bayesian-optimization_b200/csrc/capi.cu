@@ -92,7 +92,7 @@ int sbo_destroy(sbo_ctx* ctx) {
                     &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
                     &ctx->m_tgt, &ctx->partials, &ctx->result, &ctx->scan_a, &ctx->scan_b, &ctx->xs_idx, &ctx->zs_idx,
                     &ctx->xs_pay, &ctx->zs_pay, &ctx->hits, &ctx->counts, &ctx->pairctr, &ctx->imp_rows, &ctx->vx, &ctx->vz,
-                    &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err})
+                    &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v})
     free_buf(*b);
   ev_collect(ctx);
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -194,6 +194,24 @@ int sbo_set_shard(sbo_ctx* ctx, int64_t first, int64_t count) {
   SBO_REQUIRE(ctx->have_grid, "sbo_set_shard: no grid");
   SBO_REQUIRE(first >= 0 && count >= 1 && first + count <= ctx->gs.N, "shard out of range");
   ctx->gs.first = first; ctx->gs.count = count;
+  ctx->gs.cyc_n = 0; ctx->gs.cyc_rank = 0; ctx->gs.cyc_blk = 0;
+  reset_grid_state(ctx);
+  return SBO_OK;
+}
+
+int sbo_set_shard_cyclic(sbo_ctx* ctx, int rank, int nranks, int64_t block, int64_t* count_out) {
+  ENTER();
+  SBO_REQUIRE(ctx->have_grid, "sbo_set_shard_cyclic: no grid");
+  SBO_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && block >= 32 && block % 32 == 0, "bad cyclic shard");
+  GridSpec& g = ctx->gs;
+  const long long nblk = cdiv(g.N, block);
+  long long count = 0;
+  for (long long b = rank; b < nblk; b += nranks) count += (b == nblk - 1) ? (g.N - b * block) : block;
+  SBO_REQUIRE(count >= 1, "this rank owns no grid points");
+  g.first = 0; g.count = count;
+  g.cyc_n = nranks; g.cyc_rank = rank; g.cyc_blk = block;
+  if (nranks == 1) { g.cyc_n = 0; }
+  if (count_out) *count_out = count;
   reset_grid_state(ctx);
   return SBO_OK;
 }
@@ -316,6 +334,31 @@ int sbo_expander(sbo_ctx* ctx, int mode, int precision, double beta, const doubl
 int sbo_goose_target(sbo_ctx* ctx, double beta, const double* L, sbo_pair_result* out) {
   ENTER();
   return pairs_lipschitz(ctx, true, beta, L, out);
+}
+
+int sbo_pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const double* L, sbo_pairs_info* info) {
+  ENTER();
+  return pairs_prepare(ctx, mode, precision, beta, L, info);
+}
+int sbo_pairs_export_dev(sbo_ctx* ctx, void* rows_dev, void* vrows_dev) {
+  ENTER();
+  SBO_TRY(pairs_export(ctx, rows_dev, vrows_dev));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SBO_OK;
+}
+int sbo_pairs_import_dev(sbo_ctx* ctx, int64_t n_total, const void* rows_dev, const void* vrows_dev) {
+  ENTER();
+  return pairs_import(ctx, n_total, rows_dev, vrows_dev);
+}
+int sbo_pairs_run_dev(sbo_ctx* ctx, int goose, void* result_dev) {
+  ENTER();
+  SBO_TRY(pairs_run(ctx, goose, result_dev));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SBO_OK;
+}
+int sbo_pairs_finish_dev(sbo_ctx* ctx, int goose, int64_t offset, const void* result_dev, sbo_pair_result* out, int32_t* counts) {
+  ENTER();
+  return pairs_finish(ctx, goose, offset, result_dev, out, counts);
 }
 
 int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset) {

@@ -16,7 +16,9 @@ struct GridSpec {
   int kind;                 // 1 = implicit meshgrid, 2 = explicit points
   int d;
   long long N;              // global number of points
-  long long first, count;   // local shard
+  long long first, count;   // local shard: contiguous [first, first+count) ...
+  int cyc_n, cyc_rank;      // ... or block-cyclic over cyc_n ranks (cyc_n <= 1: contiguous)
+  long long cyc_blk;
   long long pts[SBO_MAX_D];
   long long stride[SBO_MAX_D];
   double lo[SBO_MAX_D], hi[SBO_MAX_D], step[SBO_MAX_D];
@@ -46,6 +48,11 @@ struct FantasyConsts {
 __device__ __forceinline__ double axis_coord(const GridSpec& g, int k, long long i) {
   if (g.pts[k] > 1 && i == g.pts[k] - 1) return g.hi[k];
   return __dadd_rn(__dmul_rn((double)i, g.step[k]), g.lo[k]);
+}
+// local shard index -> global grid index
+__device__ __host__ __forceinline__ long long shard_global(const GridSpec& g, long long p) {
+  if (g.cyc_n > 1) return ((p / g.cyc_blk) * g.cyc_n + g.cyc_rank) * g.cyc_blk + (p % g.cyc_blk);
+  return g.first + p;
 }
 // raw coordinates of GLOBAL point p
 __device__ __forceinline__ void point_coords(const GridSpec& g, long long p, double* x) {
@@ -92,6 +99,15 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// state of the staged pair driver (pairs.cu)
+struct PairStage {
+  bool prepared = false, imported = false, counted = false;
+  int mode = 0, precision = 0, row_doubles = 0;
+  double beta = 0.0;
+  double L[SBO_MAX_G] = {0, 0, 0, 0, 0, 0, 0, 0};   // L[c] for constraint c+1
+  long long nx_local = 0, nz_local = 0, nx_total = 0, pairs_evaluated = 0;
+};
+
 struct sbo_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -123,6 +139,8 @@ struct sbo_ctx {
   DevBuf vx, vz, aux_x, aux_z;
   DevBuf pp_x, pp_m, pp_v, pp_k, pp_g;   // scratch of the arbitrary-point posterior calls
   DevBuf tc_row, tc_col, tc_err;          // FP32 row/column records of the tcgen05 fantasy kernel
+  DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
+  PairStage ps;
   // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
   struct EvPair { cudaEvent_t a, b; int phase; };
   std::vector<EvPair> evlog;
@@ -182,6 +200,11 @@ int sets_pass2(sbo_ctx* ctx, double min_ucb0, sbo_sets_result* out);
 int argreduce_run(sbo_ctx* ctx, int kind, const uint32_t* mask_dev, const double* target_host, int64_t* idx, double* value);
 int compact_mask(sbo_ctx* ctx, const uint32_t* mask_dev, long long count, DevBuf& out_idx, long long* n_out);
 int pairs_lipschitz(sbo_ctx* ctx, bool goose, double beta, const double* L, sbo_pair_result* out);
+int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const double* L, sbo_pairs_info* info);
+int pairs_export(sbo_ctx* ctx, void* rows_dev, void* vrows_dev);
+int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const void* vrows_dev);
+int pairs_run(sbo_ctx* ctx, int goose, void* result_dev);
+int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_dev, sbo_pair_result* out, int32_t* counts_host);
 int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host);
 uint32_t* mask_ptr(sbo_ctx* ctx, int mask_kind, int which);
 long long mask_words(const sbo_ctx* ctx);

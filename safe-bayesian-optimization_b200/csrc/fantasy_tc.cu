@@ -13,13 +13,13 @@
 //            32 TF32 columns, STAGES-deep smem ring (full/empty mbarriers)
 //   warp 1   MMA issuer: one elected lane issues 4 x (M128,N=BN,K8) tcgen05.mma per stage; tcgen05.commit
 //            releases the smem stage and, after the last K block, publishes the TMEM accumulator slot
-//   warp 2   TMEM allocator (512 columns = 512/BN accumulator slots)
+//   warp 2   TMEM allocator (512 columns = 512/BN accumulator slots), then work-item scheduler
 //   warp 3   column-record loader: per (z tile, constraint) unit one cp.async.bulk of BN records into smem
 //   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 -> registers, fused kernel/rank-1/threshold math, per-row
 //            bitmask AND across constraints, popcount into a per-thread counter.
-// A "unit" is (z tile, constraint); TMEM slots form a ring over units so the epilogue of unit u overlaps the
-// MMAs of unit u+1.  Work items (x tile, chunk of z tiles) are rasterised so that concurrently resident CTAs
-// share z chunks (operand reuse in L2).
+// A "unit" is (tile pair, constraint); TMEM slots form a ring over units so the epilogue of unit u overlaps the
+// MMAs of unit u+1.  Work items = (x tile, z tile) pairs handed out dynamically by warp 2 (atomic counter -> smem
+// ring) in an order that keeps a group of x tiles L2-resident while the z tiles stream past.
 #include "common.cuh"
 #include <cuda.h>
 #include <math.h>
@@ -32,12 +32,13 @@ constexpr int UK = 8;          // K per tcgen05.mma kind::tf32
 constexpr int GX = 37;         // x tiles per raster group (4 z chunks in flight on 148 SMs)
 
 struct Params {
-  int nc, kblocks, nkb, npad, split, nxt, nzt, zt_per_chunk, nzc;   // kblocks = split ? 3*nkb : nkb
+  int nc, kblocks, nkb, npad, split, nxt, nzt;   // kblocks = split ? 3*nkb : nkb
   long long nx, nz, nxp, nzp, n_items;
   const float* rowrec;   // [nc][nxp][RS]
   const float* colrec;   // [nc][nzp][RS]
   int* counts;           // [nx]
   int* err;
+  unsigned int* sched_counter;   // zeroed before every launch
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,15 +121,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// work item -> (x tile, z chunk); groups of GX x tiles sweep all z chunks before the next group starts
-__device__ __forceinline__ bool item_coords(const Params& p, long long item, int& xt, int& zc) {
-  const long long per_group = (long long)GX * p.nzc;
+// work item = one (x tile, z tile) pair, all constraints.  Items are ordered so that a group of GX x tiles sweeps
+// the z tiles together: the GX*768 KB of x operands stay L2-resident while each z tile is reused by GX consecutive
+// items.  Items are handed out dynamically (atomic counter -> smem ring), which bounds the drift between CTAs to
+// about one item and keeps that reuse window intact (a static round-robin let CTAs drift apart: ncu showed 44 % L2
+// hit rate and 3 TB of DRAM reads for 5.4 GB of operands).
+__device__ __forceinline__ bool item_coords(const Params& p, long long item, int& xt, int& zt) {
+  const long long per_group = (long long)GX * p.nzt;
   const int xg = (int)(item / per_group);
   const int r = (int)(item % per_group);
-  zc = r / GX;
+  zt = r / GX;
   xt = xg * GX + r % GX;
   return xt < p.nxt;
 }
+
+constexpr int SCHED = 4;   // depth of the work-item ring
 
 template <int BN, int D4>
 struct Cfg {
@@ -137,7 +144,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = (BM + BN) * 128;   // A tile + B tile
   static constexpr int STAGES = (BN == 128) ? 5 : 4;
   static constexpr int COL_BYTES = BN * RS * 4;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * COL_BYTES + 256;
+  static constexpr int NBARS = 2 * STAGES + 2 * SLOTS + 4 + 2 * SCHED;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * COL_BYTES + 8 * NBARS + 64;
 };
 
 template <int BN, int D4>
@@ -152,7 +160,9 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t colbuf = base + STAGES * C::STAGE_BYTES;
   const float* colbuf_ptr = reinterpret_cast<const float*>(base_ptr + STAGES * C::STAGE_BYTES);
   const uint32_t bars = colbuf + 2 * C::COL_BYTES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(base_ptr + STAGES * C::STAGE_BYTES + 2 * C::COL_BYTES + 200);
+  uint8_t* tail = base_ptr + STAGES * C::STAGE_BYTES + 2 * C::COL_BYTES + 8 * C::NBARS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tail);
+  volatile int* sched_items = reinterpret_cast<volatile int*>(tail + 16);   // SCHED ints
   // barrier map (8 bytes each)
   auto bar_full = [&](int s) { return bars + 8 * s; };
   auto bar_empty = [&](int s) { return bars + 8 * (STAGES + s); };
@@ -160,6 +170,8 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto bar_tempty = [&](int s) { return bars + 8 * (2 * STAGES + SLOTS + s); };
   auto bar_cfull = [&](int b) { return bars + 8 * (2 * STAGES + 2 * SLOTS + b); };
   auto bar_cempty = [&](int b) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 2 + b); };
+  auto bar_sfull = [&](int s) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 4 + s); };
+  auto bar_sempty = [&](int s) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 4 + SCHED + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -167,6 +179,7 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 4); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull(b), 1); mbar_init(bar_cempty(b), 4); }
+    for (int s = 0; s < SCHED; ++s) { mbar_init(bar_sfull(s), 1); mbar_init(bar_sempty(s), 7); }   // 3 lanes + 4 warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -181,26 +194,53 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
+  // every consumer role walks the same ring of work items
+  int ss = 0; uint32_t sph = 0;
+  // single-lane roles call it with warp_wide = false; the epilogue warps (all lanes read the slot) sync the warp
+  // before lane 0 releases the slot
+  auto next_item = [&](bool warp_wide) -> int {
+    mbar_wait(bar_sfull(ss), sph, p.err, 7);
+    const int item = sched_items[ss];
+    if (warp_wide) __syncwarp();
+    if (!warp_wide || lane == 0) mbar_arrive(bar_sempty(ss));
+    if (++ss == SCHED) { ss = 0; sph ^= 1; }
+    return item;
+  };
+
+  if (warp == 2) {
+    // ================================ scheduler ================================
+    if (lane == 0) {
+      int s2 = 0; uint32_t ph2 = 0;
+      for (;;) {
+        long long item = (long long)atomicAdd(p.sched_counter, 1u);
+        int v = (item < p.n_items) ? (int)item : -1;
+        mbar_wait(bar_sempty(s2), ph2 ^ 1, p.err, 8);
+        sched_items[s2] = v;
+        mbar_arrive(bar_sfull(s2));
+        if (++s2 == SCHED) { s2 = 0; ph2 ^= 1; }
+        if (v < 0) break;
+      }
+    }
+  } else if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        int xt, zc;
-        if (!item_coords(p, item, xt, zc)) continue;
-        const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
-        for (int zt = zt0; zt < zt1; ++zt)
-          for (int c = 0; c < p.nc; ++c)
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(bar_empty(stage), phase ^ 1, p.err, 1);
-              mbar_expect_tx(bar_full(stage), C::STAGE_BYTES);
-              const uint32_t sa = tiles + stage * C::STAGE_BYTES;
-              // split-TF32 rows are [hi | lo]: K segments (x_hi,z_hi), (x_hi,z_lo), (x_lo,z_hi)
-              const int seg = kb / p.nkb, kk = (kb - seg * p.nkb) * BK;
-              tma_load_3d(sa, &tmA, bar_full(stage), kk + (seg == 2 ? p.npad : 0), xt * BM, c);
-              tma_load_3d(sa + BM * 128, &tmB, bar_full(stage), kk + (seg == 1 ? p.npad : 0), zt * BN, c);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
+      for (;;) {
+        const int item = next_item(false);
+        if (item < 0) break;
+        int xt, zt;
+        if (!item_coords(p, item, xt, zt)) continue;
+        for (int c = 0; c < p.nc; ++c)
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(bar_empty(stage), phase ^ 1, p.err, 1);
+            mbar_expect_tx(bar_full(stage), C::STAGE_BYTES);
+            const uint32_t sa = tiles + stage * C::STAGE_BYTES;
+            // split-TF32 rows are [hi | lo]: K segments (x_hi,z_hi), (x_hi,z_lo), (x_lo,z_hi)
+            const int seg = kb / p.nkb, kk = (kb - seg * p.nkb) * BK;
+            tma_load_3d(sa, &tmA, bar_full(stage), kk + (seg == 2 ? p.npad : 0), xt * BM, c);
+            tma_load_3d(sa + BM * 128, &tmB, bar_full(stage), kk + (seg == 1 ? p.npad : 0), zt * BN, c);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
       }
     }
   } else if (warp == 1) {
@@ -209,116 +249,115 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int slot = 0; uint32_t sphase = 0;
-      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        int xt, zc;
-        if (!item_coords(p, item, xt, zc)) continue;
-        const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
-        for (int zt = zt0; zt < zt1; ++zt)
-          for (int c = 0; c < p.nc; ++c) {
-            mbar_wait(bar_tempty(slot), sphase ^ 1, p.err, 2);
+      for (;;) {
+        const int item = next_item(false);
+        if (item < 0) break;
+        int xt, zt;
+        if (!item_coords(p, item, xt, zt)) continue;
+        for (int c = 0; c < p.nc; ++c) {
+          mbar_wait(bar_tempty(slot), sphase ^ 1, p.err, 2);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + (uint32_t)(slot * BN);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(bar_full(stage), phase, p.err, 3);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + (uint32_t)(slot * BN);
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(bar_full(stage), phase, p.err, 3);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t sa = tiles + stage * C::STAGE_BYTES;
-              const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + BM * 128);
+            const uint32_t sa = tiles + stage * C::STAGE_BYTES;
+            const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + BM * 128);
 #pragma unroll
-              for (int k = 0; k < BK / UK; ++k)
-                mma_tf32(tmem_d, adesc + (uint64_t)(k * UK * 4 / 16), bdesc + (uint64_t)(k * UK * 4 / 16), idesc,
-                         (kb | k) ? 1u : 0u);
-              mma_commit(bar_empty(stage));                 // frees the smem stage when these MMAs retire
-              if (kb == p.kblocks - 1) mma_commit(bar_tfull(slot));   // accumulator complete
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-            if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+            for (int k = 0; k < BK / UK; ++k)
+              mma_tf32(tmem_d, adesc + (uint64_t)(k * UK * 4 / 16), bdesc + (uint64_t)(k * UK * 4 / 16), idesc,
+                       (kb | k) ? 1u : 0u);
+            mma_commit(bar_empty(stage));                 // frees the smem stage when these MMAs retire
+            if (kb == p.kblocks - 1) mma_commit(bar_tfull(slot));   // accumulator complete
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+        }
       }
     }
   } else if (warp == 3) {
     // ================================ column-record loader ================================
     if (lane == 0) {
       int b = 0; uint32_t bphase = 0;
-      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        int xt, zc;
-        if (!item_coords(p, item, xt, zc)) continue;
-        const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
-        for (int zt = zt0; zt < zt1; ++zt)
-          for (int c = 0; c < p.nc; ++c) {
-            mbar_wait(bar_cempty(b), bphase ^ 1, p.err, 4);
-            mbar_expect_tx(bar_cfull(b), C::COL_BYTES);
-            bulk_load_1d(colbuf + b * C::COL_BYTES, p.colrec + ((size_t)c * p.nzp + (size_t)zt * BN) * RS, C::COL_BYTES,
-                         bar_cfull(b));
-            if (++b == 2) { b = 0; bphase ^= 1; }
-          }
+      for (;;) {
+        const int item = next_item(false);
+        if (item < 0) break;
+        int xt, zt;
+        if (!item_coords(p, item, xt, zt)) continue;
+        for (int c = 0; c < p.nc; ++c) {
+          mbar_wait(bar_cempty(b), bphase ^ 1, p.err, 4);
+          mbar_expect_tx(bar_cfull(b), C::COL_BYTES);
+          bulk_load_1d(colbuf + b * C::COL_BYTES, p.colrec + ((size_t)c * p.nzp + (size_t)zt * BN) * RS, C::COL_BYTES,
+                       bar_cfull(b));
+          if (++b == 2) { b = 0; bphase ^= 1; }
+        }
       }
     }
-  } else if (warp >= 4) {
-    // ================================ epilogue ================================
+  } else {
+    // ================================ epilogue (warps 4-7) ================================
     const int q = warp - 4;                       // TMEM lane quarter: this warp may touch lanes 32q .. 32q+31
     const int row = q * 32 + lane;
     int slot = 0; uint32_t sphase = 0;
     int b = 0; uint32_t bphase = 0;
-    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      int xt, zc;
-      if (!item_coords(p, item, xt, zc)) continue;
-      const int zt0 = zc * p.zt_per_chunk, zt1 = min(p.nzt, zt0 + p.zt_per_chunk);
+    for (;;) {
+      const int item = next_item(true);
+      if (item < 0) break;
+      int xt, zt;
+      if (!item_coords(p, item, xt, zt)) continue;
       const long long xrow = (long long)xt * BM + row;
-      int cnt = 0;
-      for (int zt = zt0; zt < zt1; ++zt) {
-        uint32_t bits[BN / 32];
+      uint32_t bits[BN / 32];
 #pragma unroll
-        for (int h = 0; h < BN / 32; ++h) bits[h] = 0xffffffffu;
-        for (int c = 0; c < p.nc; ++c) {
-          // row record of this candidate for constraint c: xx[4*D4], Cx, a, b', pad
-          float xx[4 * D4];
-          const float4* rr = reinterpret_cast<const float4*>(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
+      for (int h = 0; h < BN / 32; ++h) bits[h] = 0xffffffffu;
+      for (int c = 0; c < p.nc; ++c) {
+        // row record of this candidate for constraint c: xx[4*D4], Cx, a, b', pad
+        float xx[4 * D4];
+        const float4* rr = reinterpret_cast<const float4*>(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
 #pragma unroll
-          for (int v = 0; v < D4; ++v) {
-            const float4 t = __ldg(rr + v);
-            xx[4 * v] = t.x; xx[4 * v + 1] = t.y; xx[4 * v + 2] = t.z; xx[4 * v + 3] = t.w;
-          }
-          const float4 rt = __ldg(rr + D4);
-          const float Cx = rt.x, ax = rt.y, bx = rt.z;
-          mbar_wait(bar_cfull(b), bphase, p.err, 5);
-          mbar_wait(bar_tfull(slot), sphase, p.err, 6);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS);
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
-#pragma unroll
-          for (int h = 0; h < BN / 32; ++h) {
-            uint32_t r[32];
-            tmem_ld32(taddr + h * 32, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4* rec = cb + (size_t)(h * 32 + j) * (RS / 4);
-              const float4 tail = rec[D4];                     // Bz, m_z, s'_z, pad
-              float e = Cx - tail.x;
-#pragma unroll
-              for (int v = 0; v < D4; ++v) {
-                const float4 zc4 = rec[v];
-                e = fmaf(xx[4 * v], zc4.x, e); e = fmaf(xx[4 * v + 1], zc4.y, e);
-                e = fmaf(xx[4 * v + 2], zc4.z, e); e = fmaf(xx[4 * v + 3], zc4.w, e);
-              }
-              const float cov = ex2_approx(e) - __uint_as_float(r[j]);
-              const float mu = fmaf(cov, ax, tail.y);
-              const float t = fmaf(-(cov * cov), bx, tail.z);
-              const bool ok = (mu >= 0.f) && (mu * mu >= t);
-              w |= ok ? (1u << j) : 0u;
-            }
-            bits[h] &= w;
-          }
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) { mbar_arrive(bar_tempty(slot)); mbar_arrive(bar_cempty(b)); }
-          if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
-          if (++b == 2) { b = 0; bphase ^= 1; }
+        for (int v = 0; v < D4; ++v) {
+          const float4 t = __ldg(rr + v);
+          xx[4 * v] = t.x; xx[4 * v + 1] = t.y; xx[4 * v + 2] = t.z; xx[4 * v + 3] = t.w;
         }
+        const float4 rt = __ldg(rr + D4);
+        const float Cx = rt.x, ax = rt.y, bx = rt.z;
+        mbar_wait(bar_cfull(b), bphase, p.err, 5);
+        mbar_wait(bar_tfull(slot), sphase, p.err, 6);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
 #pragma unroll
-        for (int h = 0; h < BN / 32; ++h) cnt += __popc(bits[h]);
+        for (int h = 0; h < BN / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld32(taddr + h * 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t w = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4* rec = cb + (size_t)(h * 32 + j) * (RS / 4);
+            const float4 tail4 = rec[D4];                     // Bz, m_z, s'_z, pad
+            float e = Cx - tail4.x;
+#pragma unroll
+            for (int v = 0; v < D4; ++v) {
+              const float4 zc4 = rec[v];
+              e = fmaf(xx[4 * v], zc4.x, e); e = fmaf(xx[4 * v + 1], zc4.y, e);
+              e = fmaf(xx[4 * v + 2], zc4.z, e); e = fmaf(xx[4 * v + 3], zc4.w, e);
+            }
+            const float cov = ex2_approx(e) - __uint_as_float(r[j]);
+            const float mu = fmaf(cov, ax, tail4.y);
+            const float t = fmaf(-(cov * cov), bx, tail4.z);
+            const bool ok = (mu >= 0.f) && (mu * mu >= t);
+            w |= ok ? (1u << j) : 0u;
+          }
+          bits[h] &= w;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar_tempty(slot)); mbar_arrive(bar_cempty(b)); }
+        if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+        if (++b == 2) { b = 0; bphase ^= 1; }
       }
+      int cnt = 0;
+#pragma unroll
+      for (int h = 0; h < BN / 32; ++h) cnt += __popc(bits[h]);
       if (xrow < p.nx && cnt) atomicAdd(p.counts + xrow, cnt);
     }
   }
@@ -377,14 +416,24 @@ static int make_map(sbo_ctx* ctx, CUtensorMap* map, const float* base, int rowle
   cuuint64_t gstr[2] = {(cuuint64_t)rowlen * 4, (cuuint64_t)rows * rowlen * 4};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    const char* s = nullptr;
-    cuGetErrorString(r, &s);
-    return sbo_fail(ctx, SBO_ERR_CUDA, std::string("cuTensorMapEncodeTiled: ") + (s ? s : "?"));
+  // the driver entry point is resolved at run time so that the library has no link-time dependency on libcuda
+  // (it must load, for symbol checks, on a machine without a GPU driver)
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+      return sbo_fail(ctx, SBO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    encode = (encode_fn)fn;
   }
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return sbo_fail(ctx, SBO_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return SBO_OK;
 }
 
@@ -402,13 +451,10 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
   p.nxt = (int)cdiv(nx, BM); p.nzt = (int)cdiv(nz, BN);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  // chunk the z tiles so that there are >= ~8 items per SM, each item >= 4 z tiles when possible
-  int ztc = 32;
-  while (ztc > 4 && (long long)p.nxt * cdiv(p.nzt, ztc) < 8LL * sms) ztc /= 2;
-  p.zt_per_chunk = ztc;
-  p.nzc = (int)cdiv(p.nzt, ztc);
-  p.n_items = cdiv(p.nxt, GX) * GX * (long long)p.nzc;
+  p.n_items = cdiv(p.nxt, GX) * GX * (long long)p.nzt;
+  SBO_REQUIRE(p.n_items < 2000000000LL, "too many tile pairs for one launch");
   p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
+  p.sched_counter = (unsigned int*)(err + 1);
   static bool attr_set = false;
   if (!attr_set) {
     SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc<BN, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -431,8 +477,8 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   SBO_REQUIRE(nxp % 256 == 0 && nzp % 256 == 0, "padded row counts must be multiples of 256");
   SBO_TRY(sbo_ensure(ctx, ctx->tc_row, sizeof(float) * (size_t)nc * nxp * RS));
   SBO_TRY(sbo_ensure(ctx, ctx->tc_col, sizeof(float) * (size_t)nc * nzp * RS));
-  SBO_TRY(sbo_ensure(ctx, ctx->tc_err, sizeof(int)));
-  SBO_CUDA(cudaMemsetAsync(ctx->tc_err.p, 0, sizeof(int), ctx->stream));
+  SBO_TRY(sbo_ensure(ctx, ctx->tc_err, 2 * sizeof(int)));            // [0] error tag, [1] work-item counter
+  SBO_CUDA(cudaMemsetAsync(ctx->tc_err.p, 0, 2 * sizeof(int), ctx->stream));
   const double* xn = aux_x; const double* ax = xn + (size_t)d * nx; const double* bx = ax + (size_t)nc * nx;
   const double* zn = aux_z; const double* mz = zn + (size_t)d * nz; const double* sz = mz + (size_t)nc * nz;
   float* rowrec = (float*)ctx->tc_row.p;

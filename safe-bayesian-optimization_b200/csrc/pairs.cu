@@ -1,12 +1,20 @@
-// pairs.cu -- expander / GoOSE-target pair kernels.
+// pairs.cu -- expander / GoOSE-target pair kernels and their staged host driver.
 //   Lipschitz mode (reference-exact):  ucb_idx(x) - L*||x - z + 1e-8||_2 >= 0, x in S, z in Z
 //       models/SafeOpt.py:85-124 (Expander), models/GoOSE.py:69-114 (Target)
-//   Fantasy mode, FP64 reference kernel (north_star):
+//   Fantasy mode (north_star):
 //       c_i = k_i(z,x) - v_z.v_x ; rank-1 update of every constraint GP with y_i = ucb_i(x);
 //       z newly safe iff every updated lcb_i(z) >= 0 ; g(x) = #newly safe z.
-//   The TF32 tcgen05/TMEM version of the fantasy GEMM lives in fantasy_tc.cu.
+//       FP64 SIMT reference kernel here; the TF32 tcgen05/TMEM GEMM lives in fantasy_tc.cu.
+//
+// Host driver in five stages so that the SAME code serves one GPU and a sharded grid:
+//   prepare : compact S and Z of the local shard, build the local Z-side payload
+//   export  : write the local candidates' rows (coords, ucb, normalised coords, a, b) [+ V rows] to a buffer
+//   import  : take the rows of ALL candidates (the all-gathered exports; on one GPU: its own export)
+//   run     : pair ALL candidates with the LOCAL unsafe points -> per-candidate hit flags / newly-safe counts
+//   finish  : (after the caller all-reduced the per-candidate results) masks + arg-reductions on the local shard
 #include "common.cuh"
 #include <math.h>
+#include <string.h>
 
 #define PT 256   // threads per pair CTA = tile length of the staged side
 
@@ -15,33 +23,6 @@ struct PairConsts {
   double L[SBO_MAX_G];          // L[c] for constraint c+1
   double beta;
 };
-
-// ---------------------------------------------------------------------------------------------
-// payload gathers
-// ---------------------------------------------------------------------------------------------
-// coords[k][t] (SoA), ucb[c][t] for candidates t (local indices idx[t]); thr[c][t] = (ucb/L)^2 reach radius^2
-__global__ void __launch_bounds__(256)
-k_gather_points(GridSpec gs, int G, const long long* __restrict__ idx, long long n, const double* __restrict__ mean,
-                const double* __restrict__ var, PairConsts pc, double* __restrict__ coords, double* __restrict__ ucb,
-                double* __restrict__ thr) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const long long p = idx[t];
-  double x[SBO_MAX_D];
-  point_coords(gs, gs.first + p, x);
-  for (int k = 0; k < gs.d; ++k) coords[(size_t)k * n + t] = x[k];
-  if (ucb) {
-    for (int c = 0; c < pc.nc; ++c) {
-      const double u = ucb_of(mean[(size_t)(c + 1) * gs.count + p], var[(size_t)(c + 1) * gs.count + p], pc.beta);
-      ucb[(size_t)c * n + t] = u;
-      double r2;
-      if (!(u >= 0.0)) r2 = -1.0;
-      else if (pc.L[c] > 0.0) { const double r = u / pc.L[c]; r2 = r * r; }
-      else r2 = INFINITY;
-      thr[(size_t)c * n + t] = r2;
-    }
-  }
-}
 
 __device__ __forceinline__ bool reach_test(double s, double r2, double u, double L) {
   // exact reference predicate  u - L*sqrt(s) >= 0  (SafeOpt.py:85-88); the squared compare only
@@ -166,30 +147,6 @@ k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restri
   if (threadIdx.x == 0 && pair_counter) atomicAdd(pair_counter, tiles * (unsigned long long)PT * PT * pc.nc);
 }
 
-// hits[c][t] (per compacted element) -> bitmask words of the local shard, one mask per constraint
-__global__ void __launch_bounds__(256)
-k_hits_to_mask(int nc, long long n, const long long* __restrict__ idx, const unsigned char* __restrict__ hits,
-               uint32_t* __restrict__ masks, long long nwords) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const long long p = idx[t];
-  for (int c = 0; c < nc; ++c)
-    if (hits[(size_t)c * n + t]) atomicOr(masks + (size_t)c * nwords + (p >> 5), 1u << (p & 31));
-}
-__global__ void __launch_bounds__(256)
-k_union_count(int nc, const uint32_t* __restrict__ masks, long long nwords, unsigned long long* __restrict__ out) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned c = 0;
-  if (w < nwords) {
-    uint32_t m = 0;
-    for (int i = 0; i < nc; ++i) m |= masks[(size_t)i * nwords + w];
-    c = __popc(m);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
-}
-
 template <int D>
 static void launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long long nx, long long nz, const double* xc,
                          const double* ucb, const double* thr, const double* zc, unsigned char* hits,
@@ -207,148 +164,171 @@ static void launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long lo
     k_pairs_expander<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per);
 }
 
-int pairs_lipschitz(sbo_ctx* ctx, bool goose, double beta, const double* L, sbo_pair_result* out) {
-  SBO_REQUIRE(ctx->have_sets, "pair kernels need the sets (call sbo_sets)");
-  SBO_REQUIRE(L != nullptr, "Lipschitz constants required");
-  SBO_REQUIRE(out != nullptr, "null result");
-  const ModelSpec& ms = ctx->ms;
-  const GridSpec& gs = ctx->gs;
-  const int nc = ms.G - 1;
-  const long long count = gs.count, nw = mask_words(ctx);
-  memset(out, 0, sizeof(*out));
-  out->best_idx = -1;
-  out->best_value = goose ? INFINITY : -INFINITY;
-  for (int c = 0; c < SBO_MAX_G; ++c) { out->per_idx[c] = -1; out->per_value[c] = goose ? INFINITY : -INFINITY; }
-  DevBuf& mbuf = goose ? ctx->m_tgt : ctx->m_exp;
-  SBO_TRY(sbo_ensure(ctx, mbuf, sizeof(uint32_t) * (size_t)(nc > 0 ? nc : 1) * nw));
-  SBO_CUDA(cudaMemsetAsync(mbuf.p, 0, sizeof(uint32_t) * (size_t)(nc > 0 ? nc : 1) * nw, ctx->stream));
-  if (nc == 0) return SBO_OK;
-  PairConsts pc{};
-  pc.nc = nc; pc.beta = beta;
-  for (int c = 0; c < nc; ++c) pc.L[c] = L[c + 1];
-
-  ev_reset(ctx, 4); ev_reset(ctx, 6);
-  ev_begin(ctx, 6);
-  long long nx = 0, nz = 0;
-  SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_safe.p, count, ctx->xs_idx, &nx));
-  SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
-  out->n_x = nx; out->n_z = nz;
-  out->pairs_algorithmic = nx * nz * nc;
-  if (nx == 0 || nz == 0) { ev_end(ctx); SBO_CUDA(cudaStreamSynchronize(ctx->stream)); ev_collect(ctx); return SBO_OK; }
-  const int d = gs.d;
-  SBO_TRY(sbo_ensure(ctx, ctx->xs_pay, sizeof(double) * (size_t)nx * (d + 2 * nc)));
-  SBO_TRY(sbo_ensure(ctx, ctx->zs_pay, sizeof(double) * (size_t)nz * d));
-  const long long nh = goose ? nz : nx;
-  SBO_TRY(sbo_ensure(ctx, ctx->hits, (size_t)nc * nh));
-  SBO_TRY(sbo_ensure(ctx, ctx->pairctr, 2 * sizeof(unsigned long long)));
-  SBO_CUDA(cudaMemsetAsync(ctx->hits.p, 0, (size_t)nc * nh, ctx->stream));
-  SBO_CUDA(cudaMemsetAsync(ctx->pairctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  double* xc = (double*)ctx->xs_pay.p;
-  double* ucb = xc + (size_t)d * nx;
-  double* thr = ucb + (size_t)nc * nx;
-  double* zc = (double*)ctx->zs_pay.p;
-  k_gather_points<<<(unsigned)cdiv(nx, 256), 256, 0, ctx->stream>>>(gs, ms.G, (const long long*)ctx->xs_idx.p, nx,
-                                                                    (const double*)ctx->mean.p, (const double*)ctx->var.p,
-                                                                    pc, xc, ucb, thr);
-  SBO_LAUNCH_CHECK();
-  k_gather_points<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(gs, ms.G, (const long long*)ctx->zs_idx.p, nz,
-                                                                    (const double*)ctx->mean.p, (const double*)ctx->var.p,
-                                                                    pc, zc, nullptr, nullptr);
-  SBO_LAUNCH_CHECK();
-  ev_end(ctx);
-  unsigned long long* ctr = (unsigned long long*)ctx->pairctr.p;
-  unsigned char* hits = (unsigned char*)ctx->hits.p;
-  ev_begin(ctx, 4);
-  switch (d) {
-    case 1: launch_pairs<1>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    case 2: launch_pairs<2>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    case 3: launch_pairs<3>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    case 4: launch_pairs<4>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    case 5: launch_pairs<5>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    case 6: launch_pairs<6>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    case 7: launch_pairs<7>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-    default: launch_pairs<8>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-  }
-  SBO_LAUNCH_CHECK();
-  ev_end(ctx);
-  ev_begin(ctx, 6);
-  k_hits_to_mask<<<(unsigned)cdiv(nh, 256), 256, 0, ctx->stream>>>(nc, nh, (const long long*)(goose ? ctx->zs_idx.p : ctx->xs_idx.p),
-                                                                  hits, (uint32_t*)mbuf.p, nw);
-  SBO_LAUNCH_CHECK();
-  k_union_count<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(nc, (const uint32_t*)mbuf.p, nw, ctr + 1);
-  SBO_LAUNCH_CHECK();
-  ev_end(ctx);
-  unsigned long long h[2];
-  SBO_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
-  ev_collect(ctx);
-  out->pairs_evaluated = (int64_t)h[0] < out->pairs_algorithmic ? (int64_t)h[0] : out->pairs_algorithmic;
-  out->n_hit = (int64_t)h[1];
-  // per-constraint arg-reduction, then first-best across constraints (SafeOpt.py:120-122 / GoOSE.py:110-112)
-  const double keep5 = ctx->phase_ms[5];
-  double acc5 = 0.0;
-  for (int c = 0; c < nc; ++c) {
-    int64_t idx; double val;
-    SBO_TRY(argreduce_run(ctx, goose ? SBO_ARGMIN_LCB0 : SBO_ARGMAX_VAR0, (const uint32_t*)mbuf.p + (size_t)c * nw, nullptr, &idx, &val));
-    acc5 += ctx->phase_ms[5];
-    out->per_idx[c] = idx; out->per_value[c] = val;
-    if (idx >= 0) {
-      const bool better = out->best_idx < 0 || (goose ? (val < out->best_value) : (val > out->best_value));
-      if (better) { out->best_idx = idx; out->best_value = val; }
-    }
-  }
-  ctx->phase_ms[5] = keep5 + acc5;
-  return SBO_OK;
+// ---------------------------------------------------------------------------------------------
+// payload kernels
+// ---------------------------------------------------------------------------------------------
+// raw coordinates of compacted local points (SoA): coords[k][t]
+__global__ void __launch_bounds__(256)
+k_gather_coords(GridSpec gs, const long long* __restrict__ idx, long long n, double* __restrict__ coords) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double x[SBO_MAX_D];
+  point_coords(gs, shard_global(gs, idx[t]), x);
+  for (int k = 0; k < gs.d; ++k) coords[(size_t)k * n + t] = x[k];
 }
 
-// =============================================================================================
-// Fantasy mode, FP64 SIMT reference kernel
-// =============================================================================================
-// gather V rows of the compacted points: Vout[c][t][0..npad) = vall[c][idx[t]][0..npad)  (zero rows for padding)
+// export row of one local candidate (doubles): [coords[d] | ucb[nc] | xn[d] | a[nc] | b[nc]]
+//   a = beta*sigma/(sigma^2+sn2), b = 1/(sigma^2+sn2) in normalised units (fantasy update gains)
+__global__ void __launch_bounds__(256)
+k_export_rows(GridSpec gs, ModelSpec ms, double beta, const long long* __restrict__ idx, long long n,
+              const double* __restrict__ mean, const double* __restrict__ var, double* __restrict__ rows) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int d = gs.d, nc = ms.G - 1;
+  const int RS = 2 * d + 3 * nc;
+  const long long p = idx[t];
+  double x[SBO_MAX_D];
+  point_coords(gs, shard_global(gs, p), x);
+  double* r = rows + (size_t)t * RS;
+  for (int k = 0; k < d; ++k) { r[k] = x[k]; r[d + nc + k] = (x[k] - ms.Xmean[k]) / ms.Xstd[k]; }
+  for (int c = 0; c < nc; ++c) {
+    const double m = mean[(size_t)(c + 1) * gs.count + p], v = var[(size_t)(c + 1) * gs.count + p];
+    r[d + c] = ucb_of(m, v, beta);
+    const double ys = ms.Ystd[c + 1];
+    const double vn = v / (ys * ys);
+    const double den = vn + ms.sn2[c + 1];
+    r[2 * d + nc + c] = beta * sqrt(vn) / den;
+    r[2 * d + 2 * nc + c] = 1.0 / den;
+  }
+}
+
+// V rows of the local candidates, candidate-major: out[t][c][rowlen]
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_gather_rows(int nc, int npad, long long n, long long npadrows, long long vcount, const long long* __restrict__ idx,
+k_export_v(int nc, int rowlen, long long n, long long vcount, const long long* __restrict__ idx,
+           const T* __restrict__ vall, T* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int c = blockIdx.y;
+  if (t >= n) return;
+  const int lane = threadIdx.x & 31;
+  const T* s = vall + ((size_t)c * vcount + idx[t]) * rowlen;
+  T* o = out + ((size_t)t * nc + c) * rowlen;
+  for (int k = lane; k < rowlen; k += 32) o[k] = s[k];
+}
+
+// imported rows (AoS) -> SoA payloads of the pair kernels
+__global__ void __launch_bounds__(256)
+k_import_rows(int d, int nc, long long n, PairConsts pc, const double* __restrict__ rows, double* __restrict__ coords,
+              double* __restrict__ ucb, double* __restrict__ thr, double* __restrict__ xn, double* __restrict__ ax,
+              double* __restrict__ bx) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int RS = 2 * d + 3 * nc;
+  const double* r = rows + (size_t)t * RS;
+  for (int k = 0; k < d; ++k) { coords[(size_t)k * n + t] = r[k]; xn[(size_t)k * n + t] = r[d + nc + k]; }
+  for (int c = 0; c < nc; ++c) {
+    const double u = r[d + c];
+    ucb[(size_t)c * n + t] = u;
+    double r2;
+    if (!(u >= 0.0)) r2 = -1.0;
+    else if (pc.L[c] > 0.0) { const double q = u / pc.L[c]; r2 = q * q; }
+    else r2 = INFINITY;
+    thr[(size_t)c * n + t] = r2;
+    ax[(size_t)c * n + t] = r[2 * d + nc + c];
+    bx[(size_t)c * n + t] = r[2 * d + 2 * nc + c];
+  }
+}
+
+// imported V rows [t][c][rowlen] -> GEMM operand layout Vx[c][nxp][rowlen], zero rows for t >= n
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_import_v(int nc, int rowlen, long long n, long long npadrows, const T* __restrict__ in, T* __restrict__ vout) {
+  const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int c = blockIdx.y;
+  if (t >= npadrows) return;
+  const int lane = threadIdx.x & 31;
+  T* o = vout + ((size_t)c * npadrows + t) * rowlen;
+  if (t < n) {
+    const T* s = in + ((size_t)t * nc + c) * rowlen;
+    for (int k = lane; k < rowlen; k += 32) o[k] = s[k];
+  } else {
+    for (int k = lane; k < rowlen; k += 32) o[k] = (T)0;
+  }
+}
+
+// gather V rows of compacted LOCAL points: Vout[c][t][0..rowlen) = vall[c][idx[t]][..]  (zero rows for padding)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gather_rows(int nc, int rowlen, long long n, long long npadrows, long long vcount, const long long* __restrict__ idx,
               const T* __restrict__ vall, T* __restrict__ vout) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int c = blockIdx.y;
   if (row >= npadrows) return;
   const int lane = threadIdx.x & 31;
-  T* o = vout + ((size_t)c * npadrows + row) * npad;
+  T* o = vout + ((size_t)c * npadrows + row) * rowlen;
   if (row < n) {
-    const T* s = vall + ((size_t)c * vcount + idx[row]) * npad;
-    for (int k = lane; k < npad; k += 32) o[k] = s[k];
+    const T* s = vall + ((size_t)c * vcount + idx[row]) * rowlen;
+    for (int k = lane; k < rowlen; k += 32) o[k] = s[k];
   } else {
-    for (int k = lane; k < npad; k += 32) o[k] = (T)0;
+    for (int k = lane; k < rowlen; k += 32) o[k] = (T)0;
   }
 }
 
-// per-point auxiliaries in NORMALISED units (double):
-//  x side: xn[k][t], a[c][t] = beta*sigma/(sigma^2+sn2), b[c][t] = 1/(sigma^2+sn2)
-//  z side: zn[k][t], m[c][t] = mean_raw/Ystd,            s[c][t] = var_raw/Ystd^2
+// z-side auxiliaries in NORMALISED units: zn[k][t], m[c][t] = mean_raw/Ystd, s[c][t] = var_raw/Ystd^2
 __global__ void __launch_bounds__(256)
-k_fantasy_aux(GridSpec gs, ModelSpec ms, FantasyConsts fc, const long long* __restrict__ idx, long long n,
-              const double* __restrict__ mean, const double* __restrict__ var, int is_x,
-              double* __restrict__ xn, double* __restrict__ a, double* __restrict__ b) {
+k_fantasy_aux_z(GridSpec gs, ModelSpec ms, const long long* __restrict__ idx, long long n,
+                const double* __restrict__ mean, const double* __restrict__ var,
+                double* __restrict__ zn, double* __restrict__ m, double* __restrict__ s) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const long long p = idx[t];
   double x[SBO_MAX_D];
-  point_coords(gs, gs.first + p, x);
-  for (int k = 0; k < gs.d; ++k) xn[(size_t)k * n + t] = (x[k] - ms.Xmean[k]) / ms.Xstd[k];
-  for (int c = 0; c < fc.nc; ++c) {
+  point_coords(gs, shard_global(gs, p), x);
+  for (int k = 0; k < gs.d; ++k) zn[(size_t)k * n + t] = (x[k] - ms.Xmean[k]) / ms.Xstd[k];
+  for (int c = 0; c < ms.G - 1; ++c) {
     const double ys = ms.Ystd[c + 1];
-    const double vn = var[(size_t)(c + 1) * gs.count + p] / (ys * ys);
-    if (is_x) {
-      const double den = vn + fc.sn2[c];
-      a[(size_t)c * n + t] = fc.beta * sqrt(vn) / den;
-      b[(size_t)c * n + t] = 1.0 / den;
-    } else {
-      a[(size_t)c * n + t] = mean[(size_t)(c + 1) * gs.count + p] / ys;
-      b[(size_t)c * n + t] = vn;
-    }
+    m[(size_t)c * n + t] = mean[(size_t)(c + 1) * gs.count + p] / ys;
+    s[(size_t)c * n + t] = var[(size_t)(c + 1) * gs.count + p] / (ys * ys);
   }
 }
 
+// per-element results -> bitmask words of the local shard (one mask per constraint)
+__global__ void __launch_bounds__(256)
+k_hits_to_mask(int nc, long long n, long long stride, long long offset, const long long* __restrict__ idx,
+               const unsigned char* __restrict__ hits, uint32_t* __restrict__ masks, long long nwords) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long p = idx[t];
+  for (int c = 0; c < nc; ++c)
+    if (hits[(size_t)c * stride + offset + t]) atomicOr(masks + (size_t)c * nwords + (p >> 5), 1u << (p & 31));
+}
+__global__ void __launch_bounds__(256)
+k_counts_scatter(long long n, long long offset, const long long* __restrict__ idx, const int* __restrict__ cnt_c,
+                 int* __restrict__ cnt_pt, uint32_t* __restrict__ mask) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long p = idx[t];
+  const int c = cnt_c[offset + t];
+  if (cnt_pt) cnt_pt[p] = c;
+  if (c > 0) atomicOr(mask + (p >> 5), 1u << (p & 31));
+}
+__global__ void __launch_bounds__(256)
+k_union_count(int nc, const uint32_t* __restrict__ masks, long long nwords, unsigned long long* __restrict__ out) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned c = 0;
+  if (w < nwords) {
+    uint32_t m = 0;
+    for (int i = 0; i < nc; ++i) m |= masks[(size_t)i * nwords + w];
+    c = __popc(m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// =============================================================================================
+// Fantasy mode, FP64 SIMT reference kernel (rows = z, columns = x)
+// =============================================================================================
 #define FB 64
 #define FK 16
 template <int D>
@@ -404,7 +384,6 @@ k_fantasy_f64(FantasyConsts fc, long long nx, long long nz, long long nxp, long 
       }
       __syncthreads();
     }
-    // epilogue for constraint c
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long zi = zb + ty * 4 + i;
@@ -446,118 +425,305 @@ k_fantasy_f64(FantasyConsts fc, long long nx, long long nz, long long nxp, long 
   }
 }
 
-// counts per compacted candidate -> counts per local point + expander bitmask
-__global__ void __launch_bounds__(256)
-k_counts_scatter(long long nx, const long long* __restrict__ idx, const int* __restrict__ cnt_c, int* __restrict__ cnt_pt,
-                 uint32_t* __restrict__ mask) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nx) return;
-  const long long p = idx[t];
-  const int c = cnt_c[t];
-  if (cnt_pt) cnt_pt[p] = c;
-  if (c > 0) atomicOr(mask + (p >> 5), 1u << (p & 31));
-}
-
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
                    long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c);
 
-int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host) {
-  SBO_REQUIRE(ctx->have_sets, "fantasy expander needs the sets (call sbo_sets)");
-  SBO_REQUIRE(out != nullptr, "null result");
-  SBO_REQUIRE(precision == SBO_PREC_FP64 || precision == SBO_PREC_TF32 || precision == SBO_PREC_TF32X3, "bad precision");
+// =============================================================================================
+// staged host driver
+// =============================================================================================
+static int vrow_elems(const sbo_ctx* ctx) {   // V elements per candidate per constraint
+  return ctx->ps.precision == SBO_PREC_TF32X3 ? 2 * ctx->ms.npad : ctx->ms.npad;
+}
+static size_t v_elem_size(const sbo_ctx* ctx) { return ctx->ps.precision == SBO_PREC_FP64 ? sizeof(double) : sizeof(float); }
+
+int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const double* L, sbo_pairs_info* info) {
+  SBO_REQUIRE(ctx->have_sets, "pair kernels need the sets (call sbo_sets / sbo_sets_pass1)");
+  SBO_REQUIRE(mode == SBO_MODE_LIPSCHITZ || mode == SBO_MODE_FANTASY, "bad expander mode");
   const ModelSpec& ms = ctx->ms;
   const GridSpec& gs = ctx->gs;
-  const int nc = ms.G - 1, d = gs.d, np = ms.npad;
-  const long long count = gs.count, nw = mask_words(ctx);
-  SBO_REQUIRE(nc >= 1, "fantasy expander needs at least one constraint GP");
-  SBO_REQUIRE(ctx->keep_v == (precision == SBO_PREC_FP64 ? 1 : (precision == SBO_PREC_TF32 ? 2 : 3)),
-              "fantasy expander: run sbo_posterior with keep_v = 1 (FP64), 2 (TF32) or 3 (TF32x3) first");
-  const int rowlen = (precision == SBO_PREC_TF32X3) ? 2 * np : np;   // split rows are [hi | lo]
-  memset(out, 0, sizeof(*out));
-  out->best_idx = -1; out->best_value = -INFINITY;
-  for (int c = 0; c < SBO_MAX_G; ++c) { out->per_idx[c] = -1; out->per_value[c] = -INFINITY; }
-  SBO_TRY(sbo_ensure(ctx, ctx->m_exp, sizeof(uint32_t) * (size_t)nc * nw));
-  SBO_CUDA(cudaMemsetAsync(ctx->m_exp.p, 0, sizeof(uint32_t) * (size_t)nc * nw, ctx->stream));
-  SBO_TRY(sbo_ensure(ctx, ctx->counts, sizeof(int) * (size_t)count * 2));
-  SBO_CUDA(cudaMemsetAsync(ctx->counts.p, 0, sizeof(int) * (size_t)count * 2, ctx->stream));
-  FantasyConsts fc{};
-  fc.nc = nc; fc.d = d; fc.npad = np; fc.beta = beta;
-  for (int c = 0; c < nc; ++c) {
-    fc.sf2[c] = ms.sf2[c + 1]; fc.sn2[c] = ms.sn2[c + 1];
-    for (int k = 0; k < d; ++k) fc.inv_ell[c][k] = ms.inv_ell[c + 1][k];
+  const int nc = ms.G - 1, d = gs.d;
+  const long long count = gs.count;
+  PairStage& ps = ctx->ps;
+  ps = PairStage{};
+  ps.mode = mode; ps.precision = precision; ps.beta = beta;
+  ps.row_doubles = 2 * d + 3 * nc;
+  if (mode == SBO_MODE_LIPSCHITZ) {
+    SBO_REQUIRE(L != nullptr || nc == 0, "Lipschitz constants required");
+    for (int c = 0; c < nc; ++c) ps.L[c] = L[c + 1];
+  } else {
+    SBO_REQUIRE(nc >= 1, "fantasy expander needs at least one constraint GP");
+    SBO_REQUIRE(precision == SBO_PREC_FP64 || precision == SBO_PREC_TF32 || precision == SBO_PREC_TF32X3, "bad precision");
+    SBO_REQUIRE(ctx->keep_v == (precision == SBO_PREC_FP64 ? 1 : (precision == SBO_PREC_TF32 ? 2 : 3)),
+                "fantasy expander: run sbo_posterior with keep_v = 1 (FP64), 2 (TF32) or 3 (TF32x3) first");
   }
   ev_reset(ctx, 4); ev_reset(ctx, 6);
   ev_begin(ctx, 6);
   long long nx = 0, nz = 0;
-  SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_safe.p, count, ctx->xs_idx, &nx));
-  SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
-  out->n_x = nx; out->n_z = nz;
-  out->pairs_algorithmic = nx * nz * nc;
-  out->pairs_evaluated = nx * nz * nc;
-  if (nx == 0 || nz == 0) {
-    ev_end(ctx); SBO_CUDA(cudaStreamSynchronize(ctx->stream)); ev_collect(ctx);
-    if (counts_host) memset(counts_host, 0, sizeof(int32_t) * (size_t)count);
-    return SBO_OK;
+  if (nc > 0) {
+    SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_safe.p, count, ctx->xs_idx, &nx));
+    SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
   }
-  const long long nxp = cdiv(nx, 256) * 256, nzp = cdiv(nz, 256) * 256;
-  const size_t esz = precision == SBO_PREC_FP64 ? sizeof(double) : sizeof(float);
-  SBO_TRY(sbo_ensure(ctx, ctx->vx, esz * (size_t)nc * nxp * rowlen));
-  SBO_TRY(sbo_ensure(ctx, ctx->vz, esz * (size_t)nc * nzp * rowlen));
-  SBO_TRY(sbo_ensure(ctx, ctx->aux_x, sizeof(double) * (size_t)nx * (d + 2 * nc)));
-  SBO_TRY(sbo_ensure(ctx, ctx->aux_z, sizeof(double) * (size_t)nz * (d + 2 * nc)));
+  ps.nx_local = nx; ps.nz_local = nz;
+  if (nz > 0) {   // local Z-side payload
+    const long long* zi = (const long long*)ctx->zs_idx.p;
+    if (mode == SBO_MODE_LIPSCHITZ) {
+      SBO_TRY(sbo_ensure(ctx, ctx->zs_pay, sizeof(double) * (size_t)nz * d));
+      k_gather_coords<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(gs, zi, nz, (double*)ctx->zs_pay.p);
+      SBO_LAUNCH_CHECK();
+    } else {
+      const int rowlen = vrow_elems(ctx);
+      const long long nzp = cdiv(nz, 256) * 256;
+      SBO_TRY(sbo_ensure(ctx, ctx->vz, v_elem_size(ctx) * (size_t)nc * nzp * rowlen));
+      SBO_TRY(sbo_ensure(ctx, ctx->aux_z, sizeof(double) * (size_t)nz * (d + 2 * nc)));
+      if (precision == SBO_PREC_FP64)
+        k_gather_rows<double><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nz, nzp, count, zi, (const double*)ctx->vall.p, (double*)ctx->vz.p);
+      else
+        k_gather_rows<float><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nz, nzp, count, zi, (const float*)ctx->vall.p, (float*)ctx->vz.p);
+      SBO_LAUNCH_CHECK();
+      double* zn = (double*)ctx->aux_z.p; double* mz = zn + (size_t)d * nz; double* sz = mz + (size_t)nc * nz;
+      k_fantasy_aux_z<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(gs, ms, zi, nz, (const double*)ctx->mean.p, (const double*)ctx->var.p, zn, mz, sz);
+      SBO_LAUNCH_CHECK();
+    }
+  }
+  ev_end(ctx);
+  ps.prepared = true;
+  if (info) {
+    info->n_x_local = nx; info->n_z_local = nz; info->row_doubles = ps.row_doubles;
+    info->vrow_bytes = (mode == SBO_MODE_FANTASY) ? (int64_t)(v_elem_size(ctx) * (size_t)nc * vrow_elems(ctx)) : 0;
+  }
+  return SBO_OK;
+}
+
+int pairs_export(sbo_ctx* ctx, void* rows_dev, void* vrows_dev) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared, "sbo_pairs_export: call sbo_pairs_prepare first");
+  const long long nx = ps.nx_local;
+  if (nx == 0) return SBO_OK;
+  SBO_REQUIRE(rows_dev != nullptr, "null export buffer");
+  const ModelSpec& ms = ctx->ms;
+  const int nc = ms.G - 1;
   const long long* xi = (const long long*)ctx->xs_idx.p;
-  const long long* zi = (const long long*)ctx->zs_idx.p;
-  if (precision == SBO_PREC_FP64) {
-    k_gather_rows<double><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, np, nx, nxp, count, xi, (const double*)ctx->vall.p, (double*)ctx->vx.p);
-    SBO_LAUNCH_CHECK();
-    k_gather_rows<double><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, np, nz, nzp, count, zi, (const double*)ctx->vall.p, (double*)ctx->vz.p);
-    SBO_LAUNCH_CHECK();
-  } else {
-    k_gather_rows<float><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nx, nxp, count, xi, (const float*)ctx->vall.p, (float*)ctx->vx.p);
-    SBO_LAUNCH_CHECK();
-    k_gather_rows<float><<<dim3((unsigned)cdiv(nzp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nz, nzp, count, zi, (const float*)ctx->vall.p, (float*)ctx->vz.p);
-    SBO_LAUNCH_CHECK();
-  }
-  double* xn = (double*)ctx->aux_x.p; double* ax = xn + (size_t)d * nx; double* bx = ax + (size_t)nc * nx;
-  double* zn = (double*)ctx->aux_z.p; double* mz = zn + (size_t)d * nz; double* sz = mz + (size_t)nc * nz;
-  k_fantasy_aux<<<(unsigned)cdiv(nx, 256), 256, 0, ctx->stream>>>(gs, ms, fc, xi, nx, (const double*)ctx->mean.p, (const double*)ctx->var.p, 1, xn, ax, bx);
-  SBO_LAUNCH_CHECK();
-  k_fantasy_aux<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(gs, ms, fc, zi, nz, (const double*)ctx->mean.p, (const double*)ctx->var.p, 0, zn, mz, sz);
-  SBO_LAUNCH_CHECK();
-  ev_end(ctx);
-  int* cnt_c = (int*)ctx->counts.p;            // per compacted candidate
-  int* cnt_pt = cnt_c + count;                 // per local point
-  if (precision == SBO_PREC_FP64) {
-    ev_begin(ctx, 4);
-    dim3 grid((unsigned)cdiv(nz, FB), (unsigned)cdiv(nx, FB));
-    SBO_REQUIRE(grid.y <= 65535, "too many candidates for the FP64 fantasy kernel");
-#define FL(DD) k_fantasy_f64<DD><<<grid, 256, 0, ctx->stream>>>(fc, nx, nz, nxp, nzp, (const double*)ctx->vx.p, (const double*)ctx->vz.p, xn, ax, bx, zn, mz, sz, cnt_c)
-    switch (d) { case 1: FL(1); break; case 2: FL(2); break; case 3: FL(3); break; case 4: FL(4); break;
-                 case 5: FL(5); break; case 6: FL(6); break; case 7: FL(7); break; default: FL(8); break; }
-#undef FL
-    SBO_LAUNCH_CHECK();
-  } else {   // record prep is logged as phase 6, the GEMM kernel as phase 4 (begun inside)
-    SBO_TRY(fantasy_tc_run(ctx, fc, precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p, (const float*)ctx->vz.p,
-                           (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt_c));
-  }
-  ev_end(ctx);
   ev_begin(ctx, 6);
-  k_counts_scatter<<<(unsigned)cdiv(nx, 256), 256, 0, ctx->stream>>>(nx, xi, cnt_c, cnt_pt, (uint32_t*)ctx->m_exp.p);
+  k_export_rows<<<(unsigned)cdiv(nx, 256), 256, 0, ctx->stream>>>(ctx->gs, ms, ps.beta, xi, nx, (const double*)ctx->mean.p,
+                                                                  (const double*)ctx->var.p, (double*)rows_dev);
   SBO_LAUNCH_CHECK();
+  if (ps.mode == SBO_MODE_FANTASY) {
+    SBO_REQUIRE(vrows_dev != nullptr, "null V export buffer");
+    const int rowlen = vrow_elems(ctx);
+    if (ps.precision == SBO_PREC_FP64)
+      k_export_v<double><<<dim3((unsigned)cdiv(nx, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nx, ctx->gs.count, xi, (const double*)ctx->vall.p, (double*)vrows_dev);
+    else
+      k_export_v<float><<<dim3((unsigned)cdiv(nx, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, nx, ctx->gs.count, xi, (const float*)ctx->vall.p, (float*)vrows_dev);
+    SBO_LAUNCH_CHECK();
+  }
+  ev_end(ctx);
+  return SBO_OK;
+}
+
+int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const void* vrows_dev) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared, "sbo_pairs_import: call sbo_pairs_prepare first");
+  SBO_REQUIRE(n_total >= 0, "bad candidate count");
+  ps.nx_total = n_total;
+  ps.imported = true;
+  if (n_total == 0) return SBO_OK;
+  SBO_REQUIRE(rows_dev != nullptr, "null import buffer");
+  const ModelSpec& ms = ctx->ms;
+  const int nc = ms.G - 1, d = ctx->gs.d;
+  PairConsts pc{};
+  pc.nc = nc; pc.beta = ps.beta;
+  for (int c = 0; c < nc; ++c) pc.L[c] = ps.L[c];
+  // SoA payloads: xs_pay = coords[d] ucb[nc] thr[nc] ; aux_x = xn[d] ax[nc] bx[nc]
+  SBO_TRY(sbo_ensure(ctx, ctx->xs_pay, sizeof(double) * (size_t)n_total * (d + 2 * nc)));
+  SBO_TRY(sbo_ensure(ctx, ctx->aux_x, sizeof(double) * (size_t)n_total * (d + 2 * nc)));
+  double* xc = (double*)ctx->xs_pay.p; double* ucb = xc + (size_t)d * n_total; double* thr = ucb + (size_t)nc * n_total;
+  double* xn = (double*)ctx->aux_x.p; double* ax = xn + (size_t)d * n_total; double* bx = ax + (size_t)nc * n_total;
+  ev_begin(ctx, 6);
+  k_import_rows<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(d, nc, n_total, pc, (const double*)rows_dev, xc, ucb, thr, xn, ax, bx);
+  SBO_LAUNCH_CHECK();
+  if (ps.mode == SBO_MODE_FANTASY) {
+    SBO_REQUIRE(vrows_dev != nullptr, "null V import buffer");
+    const int rowlen = vrow_elems(ctx);
+    const long long nxp = cdiv(n_total, 256) * 256;
+    SBO_TRY(sbo_ensure(ctx, ctx->vx, v_elem_size(ctx) * (size_t)nc * nxp * rowlen));
+    if (ps.precision == SBO_PREC_FP64)
+      k_import_v<double><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, n_total, nxp, (const double*)vrows_dev, (double*)ctx->vx.p);
+    else
+      k_import_v<float><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, n_total, nxp, (const float*)vrows_dev, (float*)ctx->vx.p);
+    SBO_LAUNCH_CHECK();
+  }
+  ev_end(ctx);
+  return SBO_OK;
+}
+
+// result_dev: expander/lipschitz uint8[nc*n_total]; expander/fantasy int32[n_total]; goose: uint8[nc*nz_local]
+int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared && ps.imported, "sbo_pairs_run: prepare and import first");
+  SBO_REQUIRE(!goose || ps.mode == SBO_MODE_LIPSCHITZ, "the GoOSE target uses the Lipschitz pair test");
+  const ModelSpec& ms = ctx->ms;
+  const int nc = ms.G - 1, d = ctx->gs.d;
+  const long long nx = ps.nx_total, nz = ps.nz_local;
+  ps.pairs_evaluated = 0;
+  ps.counted = false;
+  if (nc == 0) return SBO_OK;
+  const size_t res_bytes = (ps.mode == SBO_MODE_FANTASY) ? sizeof(int) * (size_t)nx : (size_t)nc * (goose ? nz : nx);
+  if (res_bytes) {
+    SBO_REQUIRE(result_dev != nullptr, "null result buffer");
+    SBO_CUDA(cudaMemsetAsync(result_dev, 0, res_bytes, ctx->stream));
+  }
+  if (nx == 0 || nz == 0) return SBO_OK;
   SBO_TRY(sbo_ensure(ctx, ctx->pairctr, 2 * sizeof(unsigned long long)));
   SBO_CUDA(cudaMemsetAsync(ctx->pairctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  k_union_count<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(1, (const uint32_t*)ctx->m_exp.p, nw, (unsigned long long*)ctx->pairctr.p + 1);
-  SBO_LAUNCH_CHECK();
-  ev_end(ctx);
-  unsigned long long h[2];
-  SBO_CUDA(cudaMemcpyAsync(h, ctx->pairctr.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  if (counts_host) SBO_CUDA(cudaMemcpyAsync(counts_host, cnt_pt, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long* ctr = (unsigned long long*)ctx->pairctr.p;
+  const double* xc = (const double*)ctx->xs_pay.p; const double* ucb = xc + (size_t)d * nx; const double* thr = ucb + (size_t)nc * nx;
+  const double* xn = (const double*)ctx->aux_x.p; const double* ax = xn + (size_t)d * nx; const double* bx = ax + (size_t)nc * nx;
+  if (ps.mode == SBO_MODE_LIPSCHITZ) {
+    PairConsts pc{};
+    pc.nc = nc; pc.beta = ps.beta;
+    for (int c = 0; c < nc; ++c) pc.L[c] = ps.L[c];
+    const double* zc = (const double*)ctx->zs_pay.p;
+    unsigned char* hits = (unsigned char*)result_dev;
+    ev_begin(ctx, 4);
+    switch (d) {
+      case 1: launch_pairs<1>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 2: launch_pairs<2>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 3: launch_pairs<3>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 4: launch_pairs<4>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 5: launch_pairs<5>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 6: launch_pairs<6>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 7: launch_pairs<7>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      default: launch_pairs<8>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+    }
+    SBO_LAUNCH_CHECK();
+    ev_end(ctx);
+    ps.counted = true;
+  } else {
+    FantasyConsts fc{};
+    fc.nc = nc; fc.d = d; fc.npad = ms.npad; fc.beta = ps.beta;
+    for (int c = 0; c < nc; ++c) {
+      fc.sf2[c] = ms.sf2[c + 1]; fc.sn2[c] = ms.sn2[c + 1];
+      for (int k = 0; k < d; ++k) fc.inv_ell[c][k] = ms.inv_ell[c + 1][k];
+    }
+    const long long nxp = cdiv(nx, 256) * 256, nzp = cdiv(nz, 256) * 256;
+    const double* zn = (const double*)ctx->aux_z.p; const double* mz = zn + (size_t)d * nz; const double* sz = mz + (size_t)nc * nz;
+    int* cnt = (int*)result_dev;
+    if (ps.precision == SBO_PREC_FP64) {
+      dim3 grid((unsigned)cdiv(nz, FB), (unsigned)cdiv(nx, FB));
+      SBO_REQUIRE(grid.y <= 65535, "too many candidates for the FP64 fantasy kernel");
+      ev_begin(ctx, 4);
+#define FL(DD) k_fantasy_f64<DD><<<grid, 256, 0, ctx->stream>>>(fc, nx, nz, nxp, nzp, (const double*)ctx->vx.p, (const double*)ctx->vz.p, xn, ax, bx, zn, mz, sz, cnt)
+      switch (d) { case 1: FL(1); break; case 2: FL(2); break; case 3: FL(3); break; case 4: FL(4); break;
+                   case 5: FL(5); break; case 6: FL(6); break; case 7: FL(7); break; default: FL(8); break; }
+#undef FL
+      SBO_LAUNCH_CHECK();
+    } else {   // record prep is logged as phase 6, the GEMM kernel as phase 4 (begun inside)
+      SBO_TRY(fantasy_tc_run(ctx, fc, ps.precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p,
+                             (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt));
+    }
+    ev_end(ctx);
+    ps.pairs_evaluated = nx * nz * nc;
+  }
+  return SBO_OK;
+}
+
+// result_dev: the (all-reduced) per-candidate results; the local candidates are rows [offset, offset+nx_local)
+int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_dev, sbo_pair_result* out, int32_t* counts_host) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared && ps.imported, "sbo_pairs_finish: run the pair stage first");
+  SBO_REQUIRE(out != nullptr, "null result");
+  const ModelSpec& ms = ctx->ms;
+  const int nc = ms.G - 1;
+  const long long count = ctx->gs.count, nw = mask_words(ctx);
+  const long long nx = ps.nx_local, nz = ps.nz_local, nxt = ps.nx_total;
+  const bool fantasy = ps.mode == SBO_MODE_FANTASY;
+  SBO_REQUIRE(goose || (offset >= 0 && offset + nx <= nxt), "local candidate slice out of range");
+  memset(out, 0, sizeof(*out));
+  out->best_idx = -1;
+  out->best_value = goose ? INFINITY : -INFINITY;
+  for (int c = 0; c < SBO_MAX_G; ++c) { out->per_idx[c] = -1; out->per_value[c] = goose ? INFINITY : -INFINITY; }
+  out->n_x = nxt; out->n_z = nz;
+  out->pairs_algorithmic = nxt * nz * nc;
+  const int nmask = fantasy ? 1 : nc;
+  DevBuf& mbuf = goose ? ctx->m_tgt : ctx->m_exp;
+  SBO_TRY(sbo_ensure(ctx, mbuf, sizeof(uint32_t) * (size_t)(nc > 0 ? nc : 1) * nw));
+  SBO_CUDA(cudaMemsetAsync(mbuf.p, 0, sizeof(uint32_t) * (size_t)(nc > 0 ? nc : 1) * nw, ctx->stream));
+  SBO_TRY(sbo_ensure(ctx, ctx->pairctr, 2 * sizeof(unsigned long long)));
+  if (fantasy) {
+    SBO_TRY(sbo_ensure(ctx, ctx->counts, sizeof(int) * (size_t)count));
+    SBO_CUDA(cudaMemsetAsync(ctx->counts.p, 0, sizeof(int) * (size_t)count, ctx->stream));
+  }
+  unsigned long long h[2] = {0, 0};
+  const long long nloc = goose ? nz : nx;
+  const bool have = nc > 0 && nloc > 0 && nxt > 0 && nz > 0 && result_dev != nullptr;
+  if (have) {
+    ev_begin(ctx, 6);
+    const long long* idx = (const long long*)(goose ? ctx->zs_idx.p : ctx->xs_idx.p);
+    if (fantasy)
+      k_counts_scatter<<<(unsigned)cdiv(nx, 256), 256, 0, ctx->stream>>>(nx, offset, idx, (const int*)result_dev, (int*)ctx->counts.p, (uint32_t*)mbuf.p);
+    else
+      k_hits_to_mask<<<(unsigned)cdiv(nloc, 256), 256, 0, ctx->stream>>>(nc, nloc, goose ? nz : nxt, goose ? 0 : offset, idx,
+                                                                          (const unsigned char*)result_dev, (uint32_t*)mbuf.p, nw);
+    SBO_LAUNCH_CHECK();
+    unsigned long long* ctr = (unsigned long long*)ctx->pairctr.p;
+    SBO_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
+    k_union_count<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(nmask, (const uint32_t*)mbuf.p, nw, ctr + 1);
+    SBO_LAUNCH_CHECK();
+    ev_end(ctx);
+    SBO_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (counts_host) {
+    if (fantasy) SBO_CUDA(cudaMemcpyAsync(counts_host, ctx->counts.p, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    else memset(counts_host, 0, sizeof(int32_t) * (size_t)count);
+  }
   SBO_CUDA(cudaStreamSynchronize(ctx->stream));
   ev_collect(ctx);
   out->n_hit = (int64_t)h[1];
-  int64_t idx; double val;
-  SBO_TRY(argreduce_run(ctx, SBO_ARGMAX_VAR0, (const uint32_t*)ctx->m_exp.p, nullptr, &idx, &val));
-  out->per_idx[0] = idx; out->per_value[0] = val;
-  out->best_idx = idx; out->best_value = val;
+  if (ps.counted) out->pairs_evaluated = (int64_t)h[0] < out->pairs_algorithmic ? (int64_t)h[0] : out->pairs_algorithmic;
+  else out->pairs_evaluated = ps.pairs_evaluated;
+  if (!have) return SBO_OK;
+  // per-constraint arg-reduction, then first-best across constraints (SafeOpt.py:120-122 / GoOSE.py:110-112)
+  const double keep5 = ctx->phase_ms[5];
+  double acc5 = 0.0;
+  for (int c = 0; c < nmask; ++c) {
+    int64_t idx; double val;
+    SBO_TRY(argreduce_run(ctx, goose ? SBO_ARGMIN_LCB0 : SBO_ARGMAX_VAR0, (const uint32_t*)mbuf.p + (size_t)c * nw, nullptr, &idx, &val));
+    acc5 += ctx->phase_ms[5];
+    out->per_idx[c] = idx; out->per_value[c] = val;
+    if (idx >= 0) {
+      const bool better = out->best_idx < 0 || (goose ? (val < out->best_value) : (val > out->best_value));
+      if (better) { out->best_idx = idx; out->best_value = val; }
+    }
+  }
+  ctx->phase_ms[5] = keep5 + acc5;
   return SBO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-GPU compositions used by sbo_expander / sbo_goose_target: import the context's own export
+// ---------------------------------------------------------------------------------------------
+static int pairs_single(sbo_ctx* ctx, int mode, int precision, bool goose, double beta, const double* L,
+                        sbo_pair_result* out, int32_t* counts_host) {
+  SBO_REQUIRE(out != nullptr, "null result");
+  sbo_pairs_info info;
+  SBO_TRY(pairs_prepare(ctx, mode, precision, beta, L, &info));
+  const long long nx = info.n_x_local, nz = info.n_z_local;
+  const int nc = ctx->ms.G - 1;
+  SBO_TRY(sbo_ensure(ctx, ctx->exp_rows, sizeof(double) * (size_t)(nx > 0 ? nx : 1) * info.row_doubles));
+  if (mode == SBO_MODE_FANTASY) SBO_TRY(sbo_ensure(ctx, ctx->exp_v, (size_t)(nx > 0 ? nx : 1) * info.vrow_bytes));
+  SBO_TRY(pairs_export(ctx, ctx->exp_rows.p, ctx->exp_v.p));
+  SBO_TRY(pairs_import(ctx, nx, ctx->exp_rows.p, ctx->exp_v.p));
+  const size_t res_bytes = (mode == SBO_MODE_FANTASY) ? sizeof(int) * (size_t)nx : (size_t)(nc > 0 ? nc : 1) * (goose ? nz : nx);
+  SBO_TRY(sbo_ensure(ctx, ctx->hits, res_bytes));
+  SBO_TRY(pairs_run(ctx, goose ? 1 : 0, ctx->hits.p));
+  return pairs_finish(ctx, goose ? 1 : 0, 0, ctx->hits.p, out, counts_host);
+}
+
+int pairs_lipschitz(sbo_ctx* ctx, bool goose, double beta, const double* L, sbo_pair_result* out) {
+  SBO_REQUIRE(L != nullptr, "Lipschitz constants required");
+  return pairs_single(ctx, SBO_MODE_LIPSCHITZ, SBO_PREC_FP64, goose, beta, L, out, nullptr);
+}
+
+int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host) {
+  return pairs_single(ctx, SBO_MODE_FANTASY, precision, false, beta, nullptr, out, counts_host);
 }

@@ -35,7 +35,7 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
   double xn[D];
   if (ok) {
     double x[SBO_MAX_D];
-    point_coords(gs, gs.first + p0 + pl, x);
+    point_coords(gs, shard_global(gs, p0 + pl), x);
 #pragma unroll
     for (int k = 0; k < D; ++k) xn[k] = (x[k] - ms.Xmean[k]) / ms.Xstd[k];       // GP_Safe.py:326
   } else {

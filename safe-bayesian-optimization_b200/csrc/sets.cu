@@ -72,7 +72,7 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long* sm) {
 
 // pass 1: one thread per point, one ballot word per warp
 __global__ void __launch_bounds__(ST)
-k_sets_pass1(int G, long long count, long long first, const double* __restrict__ mean, const double* __restrict__ var,
+k_sets_pass1(int G, long long count, GridSpec gs, const double* __restrict__ mean, const double* __restrict__ var,
              double beta, int rule, int strict, uint32_t* __restrict__ safe_w, uint32_t* __restrict__ unsafe_w,
              SetsPartial* __restrict__ part) {
   __shared__ ArgVal sm_av[ST / 32];
@@ -91,8 +91,8 @@ k_sets_pass1(int G, long long count, long long first, const double* __restrict__
     }
     unsafe = (G > 1) && (rule == SBO_UNSAFE_ALL ? all_le : any_lt);
     if (safe) {
-      u = ArgVal{ucb_of(mean[p], var[p], beta), first + p};
-      l = ArgVal{lcb_of(mean[p], var[p], beta), first + p};
+      u = ArgVal{ucb_of(mean[p], var[p], beta), shard_global(gs, p)};
+      l = ArgVal{lcb_of(mean[p], var[p], beta), shard_global(gs, p)};
     }
   }
   const uint32_t ws = __ballot_sync(0xffffffffu, safe), wu = __ballot_sync(0xffffffffu, unsafe);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(ST) k_sets_final1(const SetsPartial* __restric
 
 // pass 2: M = S and lcb_0 <= min_ucb0 ; argmax var_0 over M
 __global__ void __launch_bounds__(ST)
-k_sets_pass2(long long count, long long first, const double* __restrict__ mean, const double* __restrict__ var,
+k_sets_pass2(long long count, GridSpec gs, const double* __restrict__ mean, const double* __restrict__ var,
              double beta, double min_ucb0, const uint32_t* __restrict__ safe_w, uint32_t* __restrict__ min_w,
              Pass2Partial* __restrict__ part) {
   __shared__ ArgVal sm_av[ST / 32];
@@ -140,7 +140,7 @@ k_sets_pass2(long long count, long long first, const double* __restrict__ mean, 
     if (safe) {
       const double lcb0 = lcb_of(mean[p], var[p], beta);
       inM = lcb0 <= min_ucb0;                                    // SafeOpt.py:62
-      if (inM) a = ArgVal{var[p], first + p};                    // SafeOpt.py:55,65
+      if (inM) a = ArgVal{var[p], shard_global(gs, p)};                    // SafeOpt.py:55,65
     }
   }
   const uint32_t wm = __ballot_sync(0xffffffffu, inM);
@@ -186,12 +186,12 @@ k_argreduce(GridSpec gs, const double* __restrict__ mean, const double* __restri
     else if (KIND == SBO_ARGMIN_UCB0) v = ucb_of(mean[p], var[p], beta);
     else {
       double x[SBO_MAX_D];
-      point_coords(gs, gs.first + p, x);
+      point_coords(gs, shard_global(gs, p), x);
       const double t[SBO_MAX_D] = {t0, t1, t2, t3, t4, t5, t6, t7};
       v = 0.0;
       for (int k = 0; k < gs.d; ++k) { const double df = x[k] - t[k]; v = __dadd_rn(v, __dmul_rn(df, df)); }   // squared distance; sqrt on host
     }
-    a = ArgVal{v, gs.first + p};
+    a = ArgVal{v, shard_global(gs, p)};
   }
   a = IS_MAX ? block_argmax(a, sm_av) : block_argmin(a, sm_av);
   if (threadIdx.x == 0) part[blockIdx.x] = RedPartial{a.v, a.i};
@@ -319,7 +319,7 @@ int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result*
   ev_reset(ctx, 3);
   ev_begin(ctx, 3);
   SBO_CUDA(cudaMemsetAsync(ctx->result.p, 0, sizeof(SetsDeviceResult), ctx->stream));
-  k_sets_pass1<<<nblocks, ST, 0, ctx->stream>>>(ctx->ms.G, count, ctx->gs.first, (const double*)ctx->mean.p,
+  k_sets_pass1<<<nblocks, ST, 0, ctx->stream>>>(ctx->ms.G, count, ctx->gs, (const double*)ctx->mean.p,
                                                 (const double*)ctx->var.p, beta, rule, strict,
                                                 (uint32_t*)ctx->m_safe.p, (uint32_t*)ctx->m_unsafe.p,
                                                 (SetsPartial*)ctx->partials.p);
@@ -345,7 +345,7 @@ int sets_pass2(sbo_ctx* ctx, double min_ucb0, sbo_sets_result* out) {
   const int nblocks = (int)cdiv(count, ST);
   SBO_TRY(sbo_ensure(ctx, ctx->partials, sizeof(SetsPartial) * (size_t)nblocks));   // >= Pass2Partial
   ev_begin(ctx, 3);
-  k_sets_pass2<<<nblocks, ST, 0, ctx->stream>>>(count, ctx->gs.first, (const double*)ctx->mean.p, (const double*)ctx->var.p,
+  k_sets_pass2<<<nblocks, ST, 0, ctx->stream>>>(count, ctx->gs, (const double*)ctx->mean.p, (const double*)ctx->var.p,
                                                 ctx->beta, min_ucb0, (const uint32_t*)ctx->m_safe.p,
                                                 (uint32_t*)ctx->m_min.p, (Pass2Partial*)ctx->partials.p);
   SBO_LAUNCH_CHECK();
