@@ -184,6 +184,11 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of k_fantasy_tc per launch from the committed ncu capture
+# (profiles/): filled in when a capture of the same configuration exists, else null
+TRAFFIC_NCU = {}
+
+
 def measure_peaks(torch, dev):
     """Yard-sticks for the roofline denominators MEASURED_PEAKS.json lacks: cuBLAS FP64 and TF32 GEMM."""
     out = {}
@@ -227,11 +232,8 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     eng = sbo_b200.GridEngine(local, stream=stream.cuda_stream)
     eng.set_grid(lo, hi, pts)
-    per = (N + world - 1) // world
-    first = rank * per
-    count = min(per, N - first)
     if world > 1:
-        eng.set_shard(first, count)
+        eng.set_shard_cyclic(rank, world, 256)      # block-cyclic ownership balances |S| and |Z| over the ranks
     fantasy = args.mode == "fantasy"
 
     def step(upload=True):
@@ -288,16 +290,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
     ex = res["expander"]
-    pairs = int(ex["pairs_algorithmic"])
-    if world > 1:
-        t = torch.tensor([pairs], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        pairs = int(t[0])
+    pairs = int(ex["pairs_algorithmic"])            # sharded.safeopt_step already returns the global count
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+    ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}     # rank 0's kernels
     peaks = {} if args.no_peaks else measure_peaks(torch, dev)
     mp = {}
     try:
@@ -309,11 +307,11 @@ def run_ours(args):
     if fantasy:
         # F_exp = pairs*(G-1)*(2n + 3d + 20), the (G-1) factor is already in `pairs`; the split-TF32 mode
         # does 3 tensor passes for the same algorithmic work, so it is charged the same flops
-        flops = pairs * (2.0 * n + 3 * d + 20)
+        flops = pairs / world * (2.0 * n + 3 * d + 20)      # rank 0's share (z is sharded evenly)
         t_k = ph["pairs"] * 1e-3
         peak = peaks.get("fp64_tflops" if args.precision == "fp64" else "tf32_tflops")
         roof = {"kernel": "fantasy expander GEMM", "bound": "tensor", "achieved": flops / t_k / 1e12 if t_k > 0 else None,
-                "peak": peak, "unit": "TFLOP/s", "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "traffic": TRAFFIC_NCU.get((args.workload, args.precision)),
                 "peak_source": "cuBLAS %s GEMM measured in this run" % ("FP64" if args.precision == "fp64" else "TF32")}
     else:
         flops = float(G) * N / world * (float(n) * n + n * (3 * d + 6))     # SURVEY 8d F_post (per rank)

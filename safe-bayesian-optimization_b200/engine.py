@@ -126,6 +126,13 @@ class GridEngine:
         self._ck(self._lib.sbo_set_shard(self._h, int(first), int(count)))
         self.first, self.count = int(first), int(count)
 
+    def set_shard_cyclic(self, rank, nranks, block=256):
+        """Block-cyclic ownership of the grid (multi-GPU): returns the number of local points."""
+        c = C.c_int64()
+        self._ck(self._lib.sbo_set_shard_cyclic(self._h, int(rank), int(nranks), int(block), C.byref(c)))
+        self.first, self.count = 0, int(c.value)
+        return self.count
+
     def point_coords(self, idx):
         x = np.empty(8)
         self._ck(self._lib.sbo_point_coords(self._h, int(idx), capi.dptr(x)))
@@ -249,6 +256,43 @@ class GridEngine:
             raise ValueError("L must have one entry per GP")
         self._ck(self._lib.sbo_goose_target(self._h, float(beta), capi.dptr(Lc), C.byref(r)))
         return self._pair_dict(r)
+
+    # -- staged pair driver (multi-GPU; tensors are torch CUDA tensors or anything with data_ptr()) --------
+    @staticmethod
+    def _ptr(t):
+        if t is None:
+            return None
+        return C.c_void_p(int(t.data_ptr())) if hasattr(t, "data_ptr") else C.c_void_p(int(t))
+
+    def pairs_prepare(self, mode, precision, beta, L=None):
+        info = capi.PairsInfo()
+        Lp = None
+        if L is not None:
+            Lc = _f64(L)
+            Lp = capi.dptr(Lc)
+        self._ck(self._lib.sbo_pairs_prepare(self._h, int(mode), int(precision), float(beta), Lp, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in capi.PairsInfo._fields_}
+
+    def pairs_export(self, rows, vrows=None):
+        self._ck(self._lib.sbo_pairs_export_dev(self._h, self._ptr(rows), self._ptr(vrows)))
+
+    def pairs_import(self, n_total, rows, vrows=None):
+        self._ck(self._lib.sbo_pairs_import_dev(self._h, int(n_total), self._ptr(rows), self._ptr(vrows)))
+
+    def pairs_run(self, goose, result):
+        self._ck(self._lib.sbo_pairs_run_dev(self._h, int(bool(goose)), self._ptr(result)))
+
+    def pairs_finish(self, goose, offset, result, want_counts=False):
+        r = capi.PairResult()
+        counts, cp = None, None
+        if want_counts:
+            counts = np.zeros(self.count, dtype=np.int32)
+            cp = counts.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self._lib.sbo_pairs_finish_dev(self._h, int(bool(goose)), int(offset), self._ptr(result), C.byref(r), cp))
+        out = self._pair_dict(r)
+        if counts is not None:
+            out["counts"] = counts
+        return out
 
     # -- whole steps (drivers' decision rules) ------------------------------------------------
     def safeopt_step(self, ds, beta, mode="lipschitz", precision="fp64", unsafe_rule=capi.UNSAFE_ALL, L=None,
