@@ -1,0 +1,145 @@
+"""GPU: the drop-in classes (reference names and signatures) drive the CUDA grid pipeline and return what the
+reference's drivers expect (test/test_SafeOpt.py:135-186, test/test_GoOSE.py:142-190), checked against the
+oracle restated on the same grid."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_ds
+
+pytestmark = pytest.mark.gpu
+
+
+def _models():
+    # reference-style import: the package directory on sys.path, then `from models import SafeOpt`
+    pkg = os.path.join(ROOT, "safe-bayesian-optimization_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from models import SafeOpt, GoOSE, GP_Safe
+    from utils import utils_SafeOpt, utils_GoOSE
+    from problems import Benoit_Problem
+    return SafeOpt, GoOSE, GP_Safe, utils_SafeOpt, utils_GoOSE, Benoit_Problem
+
+
+def test_gp_inference_single_point(oracle, c1):
+    SafeOpt, GoOSE, GP_Safe, _, _, B = _models()
+    gp = GP_Safe.GP([B.Benoit_System_1, B.con1_system_tight])
+    gp.GP_initialization(c1["X"][:9], c1["Y"][:9], 'RBF', multi_hyper=5, var_out=True, hypopt=c1["hyp_9"])
+    x = np.array([1.45698204, -0.76514894])                       # test/test_SafeOpt.py:47
+    mean, var = gp.GP_inference(x, gp.inference_datasets)
+    assert mean.shape == (2,) and var.shape == (2,) and mean.dtype == np.float64
+    mo, vo = oracle.gp_inference(x, golden_ds(oracle, c1, 9))
+    np.testing.assert_allclose(mean, mo, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(var, vo, rtol=1e-5, atol=1e-10)
+    gp.var_out = False
+    assert gp.GP_inference(x, gp.inference_datasets) == pytest.approx(mo[0], rel=1e-8)
+    # add_sample re-normalises and the next inference sees the new model (GP_Safe.py:283-304)
+    gp.var_out = True
+    gp.add_sample(c1["X"][9], c1["Y"][9], hypopt=c1["hyp_9"])
+    assert gp.n_point == 10 and gp.X_norm.shape == (10, 2) and len(gp.invKopt) == 2
+    m2, v2 = gp.GP_inference(c1["X"][9], gp.inference_datasets)
+    assert abs(m2[0] - c1["Y"][9, 0]) < 0.05 and v2[0] < 1e-2
+
+
+@pytest.mark.parametrize("n", [4, 9, 14])
+def test_safeopt_bo_api(oracle, c1, n):
+    SafeOpt, _, _, utils_SafeOpt, _, B = _models()
+    plant = [B.Benoit_System_1, B.con1_system_tight]
+    bound = np.array([[-.6, 1.5], [-1., 1.]])
+    bo = SafeOpt.BO(plant, bound, 3., grid_points_per_dim=120)
+    bo.GP_initialization(c1["X"][:n], c1["Y"][:n], 'RBF', multi_hyper=5, var_out=True, hypopt=c1[f"hyp_{n}"])
+    ds = golden_ds(oracle, c1, n)
+    pts = oracle.make_grid(bound[:, 0], bound[:, 1], [120, 120])
+    so = oracle.safeopt_step(pts, ds, 3.0, form="chol")
+    x_min, std_min = bo.Minimizer()
+    x_exp, std_exp = bo.Expander()
+    assert x_min.shape == (2,) and x_exp.shape == (2,)
+    np.testing.assert_array_equal(x_min, pts[so["minimizer_idx"]])
+    assert std_min == pytest.approx(so["minimizer_std"], rel=1e-9)
+    np.testing.assert_array_equal(x_exp, pts[so["expander_idx"]])
+    assert std_exp == pytest.approx(so["expander_std"], rel=1e-9)
+    x_u, f_u = bo.minimize_obj_ucb(None)
+    assert f_u == pytest.approx(so["min_ucb0"], rel=1e-9)
+    assert bo.maximize_infnorm_mean_grad(1) == pytest.approx(so["L"][1], rel=1e-9)
+    # scalar helpers behave like the reference's (SafeOpt.py:29-45,73-77,85-88)
+    x = np.array([0.9, -0.6])
+    mo, vo = oracle.gp_inference(x, ds)
+    assert bo.mean(x, 0) == pytest.approx(mo[0], rel=1e-8)
+    assert bo.ucb(x, 1) == pytest.approx(mo[1] + 3.0 * np.sqrt(vo[1]), rel=1e-6, abs=1e-9)
+    assert bo.lcb(x, 1) == pytest.approx(mo[1] - 3.0 * np.sqrt(vo[1]), rel=1e-6, abs=1e-9)
+    assert bo.lcb_constraint_min(x) == pytest.approx(bo.lcb(x, 1))
+    g = oracle.mean_grad(x[None, :], ds, 1)[0]
+    assert bo.infnorm_mean_grad(x, 1) == pytest.approx(np.max(np.abs(g)), rel=1e-8)
+    x2 = np.array([0.9, -0.6, 0.7, -0.2])
+    want = bo.ucb(x2[:2], 1) - 2.0 * np.linalg.norm(x2[:2] - x2[2:] + 1e-8)
+    assert bo.Lipschitz_continuity_constraint(x2, 1, 2.0) == pytest.approx(want)
+    out = bo.calculate_plant_outputs(x)
+    assert out.shape == (2,) and out[0] == pytest.approx(B.Benoit_System_1(x))
+    # driver decision (test/test_SafeOpt.py:153-158) and the plot-mask producer (test_SafeOpt.py:324-345)
+    x_new = x_min if std_min > std_exp else x_exp
+    np.testing.assert_array_equal(x_new, pts[so["x_new_idx"]])
+    X_0, X_1, mask_safe, obj = utils_SafeOpt.create_data_for_plot(bo, plant, n_grid=400)
+    assert X_0.shape == (400, 400) and mask_safe.shape == (400, 400) and mask_safe.dtype == bool
+    p400 = oracle.make_grid(bound[:, 0], bound[:, 1], [400, 400])
+    m400, v400 = oracle.posterior_chol(p400, ds)
+    want_mask = ((m400[:, 1] - 3.0 * np.sqrt(v400[:, 1])) > 0.).reshape(400, 400)
+    assert (mask_safe != want_mask).sum() <= 2
+    assert obj[3, 7] == pytest.approx(B.Benoit_System_1(np.array([X_0[3, 7], X_1[3, 7]])))
+    # the grid is restored after the plot call
+    x_min2, std_min2 = bo.Minimizer()
+    np.testing.assert_array_equal(x_min2, x_min)
+
+
+def test_goose_bo_api(oracle, c1):
+    _, GoOSE, _, _, _, B = _models()
+    plant = [B.Benoit_System_1, B.con1_system_tight]
+    bound = np.array([[-.6, 1.5], [-1., 1.]])
+    bo = GoOSE.BO(plant, bound, 3., grid_points_per_dim=100)
+    bo.GP_initialization(c1["X"][:9], c1["Y"][:9], 'RBF', multi_hyper=5, var_out=True, hypopt=c1["hyp_9"])
+    ds = golden_ds(oracle, c1, 9)
+    pts = oracle.make_grid(bound[:, 0], bound[:, 1], [100, 100])
+    go = oracle.goose_step(pts, ds, 3.0, form="chol")
+    assert len(bo.safe_set_cons) == 1
+    x_safe_min, min_safe_lcb = bo.minimize_obj_lcb()
+    x_target, target_lcb = bo.Target()
+    np.testing.assert_array_equal(x_safe_min, pts[go["safe_min_idx"]])
+    assert min_safe_lcb == pytest.approx(go["safe_min_lcb"], rel=1e-9)
+    np.testing.assert_array_equal(x_target, pts[go["target_idx"]])
+    assert target_lcb == pytest.approx(go["target_lcb"], rel=1e-9)
+    if min_safe_lcb <= target_lcb:                                   # test/test_GoOSE.py:158-162
+        x_new = x_safe_min
+    else:
+        x_new = bo.explore_safeset(x_target)
+    np.testing.assert_array_equal(x_new, pts[go["x_new_idx"]])
+    # a full SafeOpt-style loop of 3 iterations with add_sample (fixed hypers) runs end to end
+    for it in range(3):
+        x_safe_min, min_safe_lcb = bo.minimize_obj_lcb()
+        x_target, target_lcb = bo.Target()
+        x_new = x_safe_min if min_safe_lcb <= target_lcb else bo.explore_safeset(x_target)
+        y_new = bo.calculate_plant_outputs(x_new)
+        assert y_new[1] >= -0.05                                     # the queried point is (nearly) safe
+        bo.add_sample(x_new, y_new, hypopt=c1["hyp_9"])
+    assert bo.n_point == 12
+
+
+def test_wor_three_gps_fantasy_mode(oracle, c3):
+    SafeOpt, _, _, _, _, _ = _models()
+    from problems import WilliamOttoReactor_Problem
+    wo = WilliamOttoReactor_Problem.WilliamOttoReactor()
+    plant = [wo.get_objective, wo.get_constraint1, wo.get_constraint2]
+    bound = np.array([[4., 7.], [70., 100.]])
+    ds = golden_ds(oracle, c3, 20)
+    pts = oracle.make_grid(bound[:, 0], bound[:, 1], [60, 50])
+    for precision in ["fp64", "tf32x3"]:
+        bo = SafeOpt.BO(plant, bound, 2., grid_points_per_dim=[60, 50], expander_mode='fantasy', precision=precision,
+                        unsafe_rule='any')
+        bo.GP_initialization(c3["X"][:20], c3["Y"][:20], 'RBF', multi_hyper=5, var_out=True, hypopt=c3["hyp_20"])
+        x_exp, std_exp = bo.Expander()
+        so = oracle.safeopt_step(pts, ds, 2.0, mode="fantasy", unsafe_rule="any", form="chol")
+        if precision == "fp64":
+            np.testing.assert_array_equal(x_exp, pts[so["expander_idx"]])
+            assert np.array_equal(bo.safe_mask('expander'), so["expander_masks"][0])
+        assert std_exp == pytest.approx(so["expander_std"], rel=1e-6)
+        assert np.array_equal(bo.safe_mask('safe'), so["S"])
