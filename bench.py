@@ -309,10 +309,19 @@ def run_ours(args):
         # does 3 tensor passes for the same algorithmic work, so it is charged the same flops
         flops = pairs / world * (2.0 * n + 3 * d + 20)      # rank 0's share (z is sharded evenly)
         t_k = ph["pairs"] * 1e-3
-        peak = peaks.get("fp64_tflops" if args.precision == "fp64" else "tf32_tflops")
-        roof = {"kernel": "fantasy expander GEMM", "bound": "tensor", "achieved": flops / t_k / 1e12 if t_k > 0 else None,
+        if args.precision == "fp64":
+            peak, src = peaks.get("fp64_tflops"), "cuBLAS FP64 GEMM measured in this run"
+        elif mp.get("bf16_tflops_sustained"):
+            # tcgen05 kind::tf32 runs at half the dense bf16 rate; the kernel runs ~0.5 s inside a long step, so the
+            # sustained (power-capped) figure of MEASURED_PEAKS.json applies
+            peak, src = mp["bf16_tflops_sustained"] / 2.0, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate), of measured"
+        else:
+            peak, src = peaks.get("tf32_tflops"), "cuBLAS TF32 GEMM measured in this run (MEASURED_PEAKS.json absent)"
+        roof = {"kernel": "k_fantasy_tc (fantasy expander GEMM, %s)" % args.precision, "bound": "tensor",
+                "achieved": flops / t_k / 1e12 if t_k > 0 else None,
                 "peak": peak, "unit": "TFLOP/s", "traffic": TRAFFIC_NCU.get((args.workload, args.precision)),
-                "peak_source": "cuBLAS %s GEMM measured in this run" % ("FP64" if args.precision == "fp64" else "TF32")}
+                "peak_source": src, "cublas_tf32_tflops_this_run": peaks.get("tf32_tflops"),
+                "algorithmic_flops_per_launch": flops}
     else:
         flops = float(G) * N / world * (float(n) * n + n * (3 * d + 6))     # SURVEY 8d F_post (per rank)
         t_k = (ph["solve"] + ph["crosscov"]) * 1e-3

@@ -147,7 +147,7 @@ struct sbo_ctx {
   std::vector<cudaEvent_t> evpool;
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // options
-  int64_t opt_posterior_variant = 0;
+  int64_t opt_posterior_variant = 1;  // 0: FP64 SIMT register tiles, 1: FP64 tensor cores (DMMA m8n8k4)
   int64_t opt_fantasy_variant = 1;   // 0: BN=128 (4 TMEM slots), 1: BN=256 (2 slots, less operand traffic)
 };
 

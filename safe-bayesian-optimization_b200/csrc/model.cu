@@ -182,7 +182,7 @@ int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const 
   ModelSpec& ms = ctx->ms;
   memset(&ms, 0, sizeof(ms));
   ms.n = n; ms.d = d; ms.G = G;
-  ms.npad = (int)(cdiv(n, 64) * 64);
+  ms.npad = (int)(cdiv(n, 128) * 128);   // multiple of the 128-row blocks of the DMMA solve kernel
   const int np = ms.npad;
   for (int k = 0; k < d; ++k) { ms.Xmean[k] = X_mean[k]; ms.Xstd[k] = X_std[k]; }
   for (int g = 0; g < G; ++g) {

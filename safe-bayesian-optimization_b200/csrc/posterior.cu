@@ -206,6 +206,147 @@ k_solve_var(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1b (variant 1, FP64 tensor cores): the same V = W * Kx with mma.sync.m8n8k4.f64 (DMMA; sm_100a has no FP64
+// tcgen05 path).  CTA = 128 rows x 64 points per row block, 8 warps of 32x32, cp.async double-buffered K chunks of
+// 32; strides 36 / 72 doubles make the fragment loads conflict-free.  The CTA walks all row blocks so |v|^2 needs
+// no atomics; triangular in K as above.
+// ---------------------------------------------------------------------------------------------
+#define DV_BM 128
+#define DV_BP 64
+#define DV_BK 32
+#define DV_WS 36   // Ws row stride (doubles): 36 = 4 mod 16
+#define DV_KS 72   // Ks row stride (doubles): 72 = 8 mod 16
+#define DV_STAGE (DV_BM * DV_WS + DV_BK * DV_KS)
+#define DV_SMEM (2 * DV_STAGE * 8 + 4 * DV_BP * 8)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int EMIT>
+__global__ void __launch_bounds__(256, 2)
+k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, int valid,
+                 double* __restrict__ var_out, long long out_ld, void* __restrict__ vall, long long v_count) {
+  extern __shared__ __align__(16) double dsm[];
+  double* red = dsm + 2 * DV_STAGE;                 // [4][DV_BP]
+  const int g = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int wr = warp & 3, wp = warp >> 2;          // warp tile: rows wr*32.., points wp*32..
+  const int np = ms.npad;
+  const double* Wg = ms.W + (size_t)g * np * np;
+  const double* Kg = Kx + (size_t)g * np * P + (size_t)blockIdx.x * DV_BP;
+  const bool emit = (EMIT != 0) && (g > 0) && (vall != nullptr);
+  double ssum[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ssum[j][0] = ssum[j][1] = 0.0;
+
+  auto load_chunk = [&](int stage, int rb, int c0) {
+    double* Ws = dsm + stage * DV_STAGE;
+    double* Ks = Ws + DV_BM * DV_WS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                   // W tile: 128 rows x 32 cols = 2048 x 16 B
+      const int e = tid + 256 * q;
+      const int r = e >> 4, c2 = (e & 15) * 2;
+      cp_async16(Ws + r * DV_WS + c2, Wg + (size_t)(rb * DV_BM + r) * np + c0 + c2);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                   // Kx tile: 32 rows x 64 points = 1024 x 16 B
+      const int e = tid + 256 * q;
+      const int r = e >> 5, c2 = (e & 31) * 2;
+      cp_async16(Ks + r * DV_KS + c2, Kg + (size_t)(c0 + r) * P + c2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nrb = np / DV_BM;
+  for (int rb = 0; rb < nrb; ++rb) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = (rb + 1) * DV_BM / DV_BK;
+    load_chunk(0, rb, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+      if (kc + 1 < nk) {
+        load_chunk((kc + 1) & 1, rb, (kc + 1) * DV_BK);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const double* Ws = dsm + (kc & 1) * DV_STAGE;
+      const double* Ks = Ws + DV_BM * DV_WS;
+#pragma unroll
+      for (int k0 = 0; k0 < DV_BK; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Ws[(wr * 32 + i * 8 + grp) * DV_WS + k0 + tig];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncthreads();
+    }
+    // row-block epilogue: acc[i][j][e] = v[row = rb*128 + wr*32 + i*8 + grp][point = wp*32 + j*8 + 2*tig + e]
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ssum[j][e] = fma(acc[i][j][e], acc[i][j][e], ssum[j][e]);
+        if (emit) {
+          const long long pl = (long long)blockIdx.x * DV_BP + wp * 32 + j * 8 + 2 * tig + e;
+          if (pl < valid) {
+            const size_t rowbase = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * DV_BM + wr * 32 + grp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double v = acc[i][j][e];
+              if (EMIT == 1) {
+                reinterpret_cast<double*>(vall)[rowbase + i * 8] = v;
+              } else if (EMIT == 2) {
+                reinterpret_cast<float*>(vall)[rowbase + i * 8] = to_tf32((float)v);
+              } else {
+                const float hi = to_tf32((float)v);
+                reinterpret_cast<float*>(vall)[rowbase + i * 8] = hi;
+                reinterpret_cast<float*>(vall)[rowbase + i * 8 + np] = to_tf32((float)(v - (double)hi));
+              }
+            }
+          }
+        }
+      }
+  }
+  // reduce |v|^2 over the 8 lanes that share a point (same tig, all grp) and over the 4 row warps
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double s = ssum[j][e];
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if (grp == 0) red[wr * DV_BP + wp * 32 + j * 8 + 2 * tig + e] = s;
+    }
+  __syncthreads();
+  if (tid < DV_BP) {
+    const double s = red[tid] + red[DV_BP + tid] + red[2 * DV_BP + tid] + red[3 * DV_BP + tid];
+    const long long pl = (long long)blockIdx.x * DV_BP + tid;
+    if (pl < valid) {
+      const double v = fmax(0.0, ms.sf2[g] - s);                                  // GP_Safe.py:343
+      var_out[(size_t)g * out_ld + p0 + pl] = v * ms.Ystd[g] * ms.Ystd[g];        // :347
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
 template <int D>
@@ -234,6 +375,23 @@ static int crosscov_dispatch(sbo_ctx* ctx, const GridSpec& gs, long long p0, int
 
 static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, int valid, double* var_out,
                           long long out_ld, int keep_v, void* vall, long long v_count) {
+  if (ctx->opt_posterior_variant == 1) {   // FP64 tensor-core (DMMA) kernel
+    dim3 grid((unsigned)(P / DV_BP), (unsigned)ctx->ms.G);
+    static bool attr = false;
+    if (!attr) {
+      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+      attr = true;
+    }
+    if (keep_v == 1) k_solve_var_dmma<1><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    else if (keep_v == 2) k_solve_var_dmma<2><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    else if (keep_v == 3) k_solve_var_dmma<3><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    else k_solve_var_dmma<0><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
+    SBO_LAUNCH_CHECK();
+    return SBO_OK;
+  }
   dim3 grid((unsigned)(P / PB_BP), (unsigned)ctx->ms.G);
   if (keep_v == 1)
     k_solve_var<1><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
