@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "tf32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
+    ap.add_argument("--prune", type=int, default=0, help="1: also time the step with the exact z-side pruning (extra key)")
     return ap.parse_args()
 
 
@@ -290,6 +291,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
     ex = res["expander"]
+    pruned = None
+    if args.prune and fantasy:
+        eng.set_option("fantasy_prune", 1)
+        step(); barrier()
+        tp = []
+        for k in range(max(2, args.steps)):
+            flush.zero_(); barrier()
+            t0 = time.perf_counter(); rp = step(); torch.cuda.synchronize(); tp.append(time.perf_counter() - t0)
+        eng.set_option("fantasy_prune", 0)
+        pruned = {"ms_per_step": float(np.mean(tp)) * 1e3, "pairs_evaluated": int(rp["expander"]["pairs_evaluated"]),
+                  "x_new_idx": int(rp["x_new_idx"]), "n_hit": int(rp["expander"]["n_hit"]),
+                  "note": "optional exact pruning (only optimistically-safe z are paired); same sets, not the headline"}
     pairs = int(ex["pairs_algorithmic"])            # sharded.safeopt_step already returns the global count
     if rank != 0:
         if world > 1:
@@ -343,6 +356,8 @@ def run_ours(args):
             "e2e": {"value": pairs / e2e_s, "unit": "pair-evals/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "peaks": {**peaks, "hbm_gbs": mp.get("hbm_gbs"), "bf16_tflops": mp.get("bf16_tflops")}}
+    if pruned is not None:
+        line["pruned"] = pruned
     if not args.no_cpu_baseline and world == 1:
         s = cpu_sample_step(ds, lo, hi, pts, beta, args.mode)
         t_full = cpu_extrapolate(s, N, pairs)

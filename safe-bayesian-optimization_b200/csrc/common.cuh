@@ -105,7 +105,7 @@ struct PairStage {
   int mode = 0, precision = 0, row_doubles = 0;
   double beta = 0.0;
   double L[SBO_MAX_G] = {0, 0, 0, 0, 0, 0, 0, 0};   // L[c] for constraint c+1
-  long long nx_local = 0, nz_local = 0, nx_total = 0, pairs_evaluated = 0;
+  long long nx_local = 0, nz_local = 0, nz_full = 0, nx_total = 0, pairs_evaluated = 0;   // nz_local <= nz_full when pruned
 };
 
 struct sbo_ctx {
@@ -148,7 +148,10 @@ struct sbo_ctx {
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // options
   int64_t opt_posterior_variant = 1;  // 0: FP64 SIMT register tiles, 1: FP64 tensor cores (DMMA m8n8k4)
-  int64_t opt_fantasy_variant = 1;   // 0: BN=128 (4 TMEM slots), 1: BN=256 (2 slots, less operand traffic)
+  int64_t opt_fantasy_prune = 0;      // 1: pair only the optimistically-safe part of Z (exact, see k_prune_unsafe)
+  long long n_unsafe_local = 0;
+  DevBuf m_prune;
+  int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps
 };
 
 extern thread_local std::string g_sbo_last_error;

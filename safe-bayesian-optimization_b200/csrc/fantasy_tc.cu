@@ -148,8 +148,8 @@ struct Cfg {
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * COL_BYTES + 8 * NBARS + 64;
 };
 
-template <int BN, int D4>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int D4, int EW>   // EW = epilogue warps (4 or 8): 8 puts two warps on every scheduler and splits the columns
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN, D4>;
   constexpr int RS = C::RS, SLOTS = C::SLOTS, STAGES = C::STAGES;
@@ -177,9 +177,9 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 4); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull(b), 1); mbar_init(bar_cempty(b), 4); }
-    for (int s = 0; s < SCHED; ++s) { mbar_init(bar_sfull(s), 1); mbar_init(bar_sempty(s), 7); }   // 3 lanes + 4 warps
+    for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), EW); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull(b), 1); mbar_init(bar_cempty(b), EW); }
+    for (int s = 0; s < SCHED; ++s) { mbar_init(bar_sfull(s), 1); mbar_init(bar_sempty(s), 3 + EW); }   // 3 lanes + EW warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -294,8 +294,10 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ================================ epilogue (warps 4-7) ================================
-    const int q = warp - 4;                       // TMEM lane quarter: this warp may touch lanes 32q .. 32q+31
+    // ================================ epilogue (warps 4 .. 4+EW-1) ================================
+    const int q = warp & 3;                       // TMEM lane quarter: a warp may touch lanes 32*(warp%4) .. +31
+    const int half = (warp - 4) >> 2;             // EW = 8: warps 8-11 take the upper half of the columns
+    constexpr int NCH = BN / 32 / (EW / 4);       // 32-column chunks per warp per unit
     const int row = q * 32 + lane;
     int slot = 0; uint32_t sphase = 0;
     int b = 0; uint32_t bphase = 0;
@@ -305,9 +307,9 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int xt, zt;
       if (!item_coords(p, item, xt, zt)) continue;
       const long long xrow = (long long)xt * BM + row;
-      uint32_t bits[BN / 32];
+      uint32_t bits[NCH];
 #pragma unroll
-      for (int h = 0; h < BN / 32; ++h) bits[h] = 0xffffffffu;
+      for (int h = 0; h < NCH; ++h) bits[h] = 0xffffffffu;
       for (int c = 0; c < p.nc; ++c) {
         // row record of this candidate for constraint c: xx[4*D4], Cx, a, b', pad
         float xx[4 * D4];
@@ -322,10 +324,10 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(bar_cfull(b), bphase, p.err, 5);
         mbar_wait(bar_tfull(slot), sphase, p.err, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN);
+        const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS) + (size_t)half * NCH * 32 * (RS / 4);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + half * NCH * 32);
 #pragma unroll
-        for (int h = 0; h < BN / 32; ++h) {
+        for (int h = 0; h < NCH; ++h) {
           uint32_t r[32];
           tmem_ld32(taddr + h * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -357,7 +359,7 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       int cnt = 0;
 #pragma unroll
-      for (int h = 0; h < BN / 32; ++h) cnt += __popc(bits[h]);
+      for (int h = 0; h < NCH; ++h) cnt += __popc(bits[h]);
       if (xrow < p.nx && cnt) atomicAdd(p.counts + xrow, cnt);
     }
   }
@@ -437,7 +439,7 @@ static int make_map(sbo_ctx* ctx, CUtensorMap* map, const float* base, int rowle
   return SBO_OK;
 }
 
-template <int BN, int D4>
+template <int BN, int D4, int EW>
 static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
                   const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err) {
   using C = Cfg<BN, D4>;
@@ -457,11 +459,11 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
   p.sched_counter = (unsigned int*)(err + 1);
   static bool attr_set = false;
   if (!attr_set) {
-    SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc<BN, D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc<BN, D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = (int)((p.n_items < sms) ? p.n_items : sms);
-  k_fantasy_tc<BN, D4><<<grid, 256, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+  k_fantasy_tc<BN, D4, EW><<<grid, 128 + 32 * EW, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
   SBO_LAUNCH_CHECK();
   return SBO_OK;
 }
@@ -496,15 +498,28 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
     SBO_LAUNCH_CHECK();
   }
   int* err = (int*)ctx->tc_err.p;
-  const bool wide = ctx->opt_fantasy_variant == 1;
+  // variant: bit 0: BN = 256, bit 1: 8 epilogue warps; < 0 = auto: BN = 256 (less operand traffic); 8 epilogue warps
+  // when the epilogue outweighs the MMAs (short K) or carries 12-float records (d > 4)
+  int variant = (int)ctx->opt_fantasy_variant;
+  if (variant < 0) variant = 1 | ((fc.npad <= 256 || D4 == 2) ? 2 : 0);
   ev_end(ctx);            // record prep = phase 6
   ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)
+#define TC_LAUNCH(BN_, D4_, EW_) SBO_TRY((tc::launch<BN_, D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)))
   if (D4 == 1) {
-    if (wide) SBO_TRY((tc::launch<256, 1>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
-    else SBO_TRY((tc::launch<128, 1>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
+    switch (variant & 3) {
+      case 0: TC_LAUNCH(128, 1, 4); break;
+      case 1: TC_LAUNCH(256, 1, 4); break;
+      case 2: TC_LAUNCH(128, 1, 8); break;
+      default: TC_LAUNCH(256, 1, 8); break;
+    }
   } else {
-    if (wide) SBO_TRY((tc::launch<256, 2>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
-    else SBO_TRY((tc::launch<128, 2>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)));
+    switch (variant & 3) {
+      case 0: TC_LAUNCH(128, 2, 4); break;
+      case 1: TC_LAUNCH(256, 2, 4); break;
+      case 2: TC_LAUNCH(128, 2, 8); break;
+      default: TC_LAUNCH(256, 2, 8); break;
+    }
   }
+#undef TC_LAUNCH
   return SBO_OK;
 }

@@ -292,6 +292,25 @@ k_fantasy_aux_z(GridSpec gs, ModelSpec ms, const long long* __restrict__ idx, lo
   }
 }
 
+// exact pruning of the z side of the fantasy expander: |cov(z,x)| <= sigma_z*sigma_x (posterior covariance is PSD)
+// gives mu'_c <= m_z + beta*sigma_z for every candidate x, so an unsafe z with ucb_c(z) < 0 for some constraint can
+// never become safe whatever x is observed.  Only the "optimistically safe" part of Z is paired.
+__global__ void __launch_bounds__(256)
+k_prune_unsafe(int G, long long count, const double* __restrict__ mean, const double* __restrict__ var, double beta,
+               double tol, ModelSpec ms, const uint32_t* __restrict__ unsafe_w, uint32_t* __restrict__ out_w) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (p < count && ((unsafe_w[p >> 5] >> (p & 31)) & 1u)) {
+    keep = true;
+    for (int i = 1; i < G; ++i) {
+      const double u = mean[(size_t)i * count + p] + beta * sqrt(var[(size_t)i * count + p]) * (1.0 + tol);
+      keep = keep && (u >= -tol * ms.Ystd[i]);
+    }
+  }
+  const uint32_t w = __ballot_sync(0xffffffffu, keep);
+  if ((threadIdx.x & 31) == 0 && p < count) out_w[p >> 5] = w;
+}
+
 // per-element results -> bitmask words of the local shard (one mask per constraint)
 __global__ void __launch_bounds__(256)
 k_hits_to_mask(int nc, long long n, long long stride, long long offset, const long long* __restrict__ idx,
@@ -459,9 +478,21 @@ int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const doub
   ev_reset(ctx, 4); ev_reset(ctx, 6);
   ev_begin(ctx, 6);
   long long nx = 0, nz = 0;
+  ps.nz_full = 0;
   if (nc > 0) {
     SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_safe.p, count, ctx->xs_idx, &nx));
-    SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
+    if (mode == SBO_MODE_FANTASY && ctx->opt_fantasy_prune) {
+      const long long nw = mask_words(ctx);
+      SBO_TRY(sbo_ensure(ctx, ctx->m_prune, sizeof(uint32_t) * nw));
+      k_prune_unsafe<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ms.G, count, (const double*)ctx->mean.p, (const double*)ctx->var.p,
+                                                                         beta, 1e-6, ms, (const uint32_t*)ctx->m_unsafe.p, (uint32_t*)ctx->m_prune.p);
+      SBO_LAUNCH_CHECK();
+      SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_prune.p, count, ctx->zs_idx, &nz));
+      ps.nz_full = ctx->n_unsafe_local;
+    } else {
+      SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
+      ps.nz_full = nz;
+    }
   }
   ps.nx_local = nx; ps.nz_local = nz;
   if (nz > 0) {   // local Z-side payload
@@ -488,7 +519,7 @@ int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const doub
   ev_end(ctx);
   ps.prepared = true;
   if (info) {
-    info->n_x_local = nx; info->n_z_local = nz; info->row_doubles = ps.row_doubles;
+    info->n_x_local = nx; info->n_z_local = ps.nz_full; info->row_doubles = ps.row_doubles;
     info->vrow_bytes = (mode == SBO_MODE_FANTASY) ? (int64_t)(v_elem_size(ctx) * (size_t)nc * vrow_elems(ctx)) : 0;
   }
   return SBO_OK;
@@ -642,8 +673,8 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
   out->best_idx = -1;
   out->best_value = goose ? INFINITY : -INFINITY;
   for (int c = 0; c < SBO_MAX_G; ++c) { out->per_idx[c] = -1; out->per_value[c] = goose ? INFINITY : -INFINITY; }
-  out->n_x = nxt; out->n_z = nz;
-  out->pairs_algorithmic = nxt * nz * nc;
+  out->n_x = nxt; out->n_z = ps.nz_full;                 // |Z| of the local shard; nz = what was actually paired
+  out->pairs_algorithmic = nxt * ps.nz_full * nc;
   const int nmask = fantasy ? 1 : nc;
   DevBuf& mbuf = goose ? ctx->m_tgt : ctx->m_exp;
   SBO_TRY(sbo_ensure(ctx, mbuf, sizeof(uint32_t) * (size_t)(nc > 0 ? nc : 1) * nw));

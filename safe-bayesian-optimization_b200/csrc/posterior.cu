@@ -282,6 +282,9 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
       __syncthreads();
       const double* Ws = dsm + (kc & 1) * DV_STAGE;
       const double* Ks = Ws + DV_BM * DV_WS;
+      // W is lower triangular: this warp's 32 rows need columns <= rb*128 + wr*32 + 31 only, i.e. K chunks
+      // kc <= rb*4 + wr; the later chunks of the diagonal block are all zeros for it
+      if (kc <= rb * (DV_BM / DV_BK) + wr)
 #pragma unroll
       for (int k0 = 0; k0 < DV_BK; k0 += 4) {
         double a[4], b[4];

@@ -333,6 +333,7 @@ int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result*
   ev_collect(ctx);
   r.max_var = -INFINITY; r.max_var_i = -1; r.n_min = 0;
   if (out) fill_result(r, out);
+  ctx->n_unsafe_local = r.n_unsafe;
   ctx->beta = beta;
   ctx->have_sets = true;
   ctx->have_sets2 = false;

@@ -456,7 +456,7 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
     m, v = engine.posterior(keep_v=keep_v)
     engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
     ex = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
-    engine.set_option("fantasy_variant", 1)
+    engine.set_option("fantasy_variant", -1)
     pts = oracle.make_grid(lo, hi, grid)
     lcb, _ = oracle.bounds(m, v, beta)
     S, Z = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, rule)
@@ -494,7 +494,7 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("name,n,beta,grid,rule", [("c1", 9, 3.0, [48, 40], "all"), ("c3", 20, 2.0, [45, 61], "any"),
                                                     ("c3", 35, 2.0, [70, 50], "all")])
 def test_fantasy_tensor_core_counts(engine, oracle, request, name, n, beta, grid, rule, variant, precision):
@@ -505,7 +505,7 @@ def test_fantasy_tensor_core_counts(engine, oracle, request, name, n, beta, grid
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_fantasy_tensor_core_synthetic(engine, oracle, variant, precision):
     from sbo_b200 import workloads
     for (d, ppd, n, G) in [(3, 14, 70, 3), (4, 9, 200, 4), (6, 5, 130, 3)]:

@@ -1,0 +1,35 @@
+"""GPU: the optional exact pruning of the fantasy expander's z side (option fantasy_prune, k_prune_unsafe) must not
+change any count: an unsafe z with ucb_c(z) < 0 for some constraint can never become safe (|cov| <= sigma_z sigma_x)."""
+import numpy as np
+import pytest
+
+from conftest import golden_ds
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("precision", ["fp64", "tf32x3"])
+def test_prune_is_exact(engine, oracle, c3, precision):
+    from sbo_b200 import _capi as capi, workloads
+    prec, keep_v = capi.PRECISIONS[precision]
+    cases = [(golden_ds(oracle, c3, 20), c3["lo"], c3["hi"], [40, 44], 2.0, capi.UNSAFE_ANY)]
+    ds, lo, hi, ppd, beta = workloads.small(d=4, pts_per_dim=9, n=200, seed=11, G=4)
+    cases.append((ds, lo, hi, ppd, beta, capi.UNSAFE_ALL))
+    cases.append((ds, lo, hi, ppd, beta, capi.UNSAFE_ANY))
+    for ds, lo, hi, grid, beta, rule in cases:
+        engine.set_model(ds)
+        engine.set_grid(lo, hi, grid)
+        engine.posterior(keep_v=keep_v, fetch=False)
+        engine.sets(beta, rule)
+        try:
+            engine.set_option("fantasy_prune", 0)
+            full = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+            engine.set_option("fantasy_prune", 1)
+            pruned = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+        finally:
+            engine.set_option("fantasy_prune", 0)
+        assert np.array_equal(full["counts"], pruned["counts"])
+        assert full["best_idx"] == pruned["best_idx"] and full["n_hit"] == pruned["n_hit"]
+        assert full["n_z"] == pruned["n_z"] and full["pairs_algorithmic"] == pruned["pairs_algorithmic"]
+        assert pruned["pairs_evaluated"] <= full["pairs_evaluated"]
+        print(f"prune {precision}: pairs evaluated {pruned['pairs_evaluated']} of {full['pairs_evaluated']}, newly-safe total {int(full['counts'].sum())}")
