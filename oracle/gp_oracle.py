@@ -7,15 +7,19 @@ only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``safe-bayesian-optimization_b200/`` imports it; the product path has no CPU
 fallback.
 
-PARITY UNPINNED.  The reference cannot be imported here (it needs ``jax`` and
-``sobol_seq``, both absent, no network) and its own tests contain no assertions
-or golden vectors, so there is nothing reference-produced
-to pin this restatement against.  Every function cites the reference lines it
-follows; the restatement is validated by internal consistency only:
-inverse-form vs Cholesky-form posterior, rank-1 fantasy update vs re-running the
-inference on the augmented data set, analytic gradient vs central differences,
-and the properties the reference's scripts print (interpolation at a training
-point, constraint prior mean far from the data).
+PARITY PINNED against outputs of the reference's own source (with one stated gap).  JAX is not installed here, so
+``tests/golden/make_reference_vectors.py`` imports the UNMODIFIED ``/root/reference/models/{GP_Safe,SafeOpt,
+GoOSE}.py`` over a NumPy-backed ``jax`` stand-in (``tests/golden/refshim/``) and records what the reference computes:
+its DE hyper-fit, ``invKopt``, normalisation, single-point ``GP_inference``/``lcb``/``ucb``/``infnorm_mean_grad``,
+the 400x400 plot mask of ``create_data_for_plot`` and the DE-based ``Minimizer/Expander/Target/explore_safeset``
+(committed as ``tests/golden/ref_*.npz``).  ``tests/test_reference_vectors.py`` checks this restatement against them:
+model state bit-for-bit (normalisation, K, inv(K)), posterior to 1e-9 scale-relative, plot mask identical, DE
+optima by containment up to the grid resolution.  The gap: the arithmetic backend of those vectors is NumPy/LAPACK
+FP64, not XLA-CPU, so XLA's rounding is not pinned.  The fantasy expander (``fantasy_*``) is not in the reference
+at all (north_star addition): it stays UNPINNED and is validated by re-running the pinned inference on the
+augmented (n+1)-point data set.  Every function cites the reference lines it follows; internal consistency checks
+(inverse-form vs Cholesky-form posterior, analytic gradient vs central differences, the properties the reference's
+scripts print) are in ``tests/test_oracle.py``.
 
 Conventions
 -----------

@@ -380,6 +380,7 @@ int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value) {
   SBO_REQUIRE(name != nullptr, "null option name");
   if (!strcmp(name, "posterior_variant")) { ctx->opt_posterior_variant = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_variant")) { ctx->opt_fantasy_variant = value; return SBO_OK; }
+  if (!strcmp(name, "fantasy_gx")) { ctx->opt_fantasy_gx = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_prune")) { ctx->opt_fantasy_prune = value; return SBO_OK; }
   return sbo_fail(ctx, SBO_ERR_INVALID, std::string("unknown option ") + name);
 }

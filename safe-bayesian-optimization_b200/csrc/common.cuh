@@ -151,7 +151,9 @@ struct sbo_ctx {
   int64_t opt_fantasy_prune = 0;      // 1: pair only the optimistically-safe part of Z (exact, see k_prune_unsafe)
   long long n_unsafe_local = 0;
   DevBuf m_prune;
-  int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps
+  int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps;
+                                     // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
+  int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };
 
 extern thread_local std::string g_sbo_last_error;

@@ -33,6 +33,7 @@ constexpr int GX = 37;         // x tiles per raster group (4 z chunks in flight
 
 struct Params {
   int nc, kblocks, nkb, npad, split, nxt, nzt;   // kblocks = split ? 3*nkb : nkb
+  int gx;                                        // x tiles per raster group (2-CTA kernel; the 1-CTA kernel uses GX)
   long long nx, nz, nxp, nzp, n_items;
   const float* rowrec;   // [nc][nxp][RS]
   const float* colrec;   // [nc][nzp][RS]
@@ -372,6 +373,329 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+// =============================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile pair with ONE
+// tcgen05.mma M=256 stream issued by the leader CTA (cluster rank 0).  Each CTA stages only its own half of both
+// operands per K block -- 128 candidate rows (A half) + 128 unsafe rows (B half) = 32 KB instead of 48 KB -- so the
+// L2->SM operand traffic per MMA drops by a third and the same shared memory holds 6 stages instead of 4.
+// Each CTA's TMEM holds the accumulator rows of ITS 128 candidates for all 256 z columns; the epilogue is the
+// 1-CTA BN=256 epilogue unchanged.
+//   full[s]    leader's barrier: leader's producer arms 64 KB, both CTAs' TMA (.cta_group::2) complete_tx on it
+//   empty[s]   per CTA, armed by the leader's tcgen05.commit.cta_group::2 multicast (mask 0b11)
+//   tfull[t]   per CTA, same multicast commit after the last K block;  tempty[t]: leader's, 2*EW remote arrivals
+//   work items one scheduler (leader, warp 2) -> both CTAs' item rings (st.shared::cluster + remote arrive)
+// =============================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cl(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity, int* err, int tag) {
+  if (mbar_try_cl(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_cl(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      if (err) atomicExch(err, tag);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+template <int D4>
+struct Cfg2 {
+  static constexpr int BN = 256;                        // z columns per tile pair (128 staged by each CTA)
+  static constexpr int RS = 4 * D4 + 4;
+  static constexpr int SLOTS = 2;                       // 512 TMEM columns / 256
+  static constexpr int STAGE_BYTES = (BM + BN / 2) * 128;   // per CTA: A half + B half = 32 KB
+  static constexpr int STAGES = 6;
+  static constexpr int COL_BYTES = BN * RS * 4;
+  static constexpr int NBARS = 2 * STAGES + 2 * SLOTS + 4 + 2 * SCHED;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * COL_BYTES + 8 * NBARS + 64;
+};
+
+// work item = (256-row x tile pair, 256-column z tile); p.gx x tile pairs sweep the z tiles together
+__device__ __forceinline__ bool item_coords2(const Params& p, long long item, int& xt, int& zt) {
+  const long long per_group = (long long)p.gx * p.nzt;
+  const int xg = (int)(item / per_group);
+  const int r = (int)(item % per_group);
+  zt = r / p.gx;
+  xt = xg * p.gx + r % p.gx;
+  return xt < p.nxt;
+}
+
+template <int D4, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
+k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg2<D4>;
+  constexpr int BN = C::BN, RS = C::RS, SLOTS = C::SLOTS, STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t tiles = base;
+  const uint32_t colbuf = base + STAGES * C::STAGE_BYTES;
+  const float* colbuf_ptr = reinterpret_cast<const float*>(base_ptr + STAGES * C::STAGE_BYTES);
+  const uint32_t bars = colbuf + 2 * C::COL_BYTES;
+  uint8_t* tail = base_ptr + STAGES * C::STAGE_BYTES + 2 * C::COL_BYTES + 8 * C::NBARS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tail);
+  volatile int* sched_items = reinterpret_cast<volatile int*>(tail + 16);
+  auto bar_full = [&](int s) { return bars + 8 * s; };
+  auto bar_empty = [&](int s) { return bars + 8 * (STAGES + s); };
+  auto bar_tfull = [&](int s) { return bars + 8 * (2 * STAGES + s); };
+  auto bar_tempty = [&](int s) { return bars + 8 * (2 * STAGES + SLOTS + s); };
+  auto bar_cfull = [&](int b) { return bars + 8 * (2 * STAGES + 2 * SLOTS + b); };
+  auto bar_cempty = [&](int b) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 2 + b); };
+  auto bar_sfull = [&](int s) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 4 + s); };
+  auto bar_sempty = [&](int s) { return bars + 8 * (2 * STAGES + 2 * SLOTS + 4 + SCHED + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < SLOTS; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 2 * EW); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_cfull(b), 1); mbar_init(bar_cempty(b), EW); }
+    // consumers of a work item: leader = producer, MMA, column loader + EW epilogue warps; peer = the same minus MMA
+    for (int s = 0; s < SCHED; ++s) { mbar_init(bar_sfull(s), 1); mbar_init(bar_sempty(s), 5 + 2 * EW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before anything is signalled across the pair
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_holder;
+
+  int ss = 0; uint32_t sph = 0;
+  auto next_item = [&](bool warp_wide) -> int {
+    mbar_wait_cl(bar_sfull(ss), sph, p.err, 7);
+    const int item = sched_items[ss];
+    if (warp_wide) __syncwarp();
+    if (!warp_wide || lane == 0) mbar_arrive_cluster(mapa_u32(bar_sempty(ss), 0));
+    if (++ss == SCHED) { ss = 0; sph ^= 1; }
+    return item;
+  };
+
+  if (warp == 2) {
+    // ================================ scheduler (leader CTA only) ================================
+    if (lane == 0 && rank == 0) {
+      int s2 = 0; uint32_t ph2 = 0;
+      const uint32_t peer_items = mapa_u32(smem_u32(const_cast<int*>(sched_items)), 1);
+      for (;;) {
+        long long item = (long long)atomicAdd(p.sched_counter, 1u);
+        int v = (item < p.n_items) ? (int)item : -1;
+        mbar_wait_cl(bar_sempty(s2), ph2 ^ 1, p.err, 8);
+        sched_items[s2] = v;
+        st_cluster_u32(peer_items + 4 * s2, (uint32_t)v);
+        mbar_arrive(bar_sfull(s2));
+        mbar_arrive_cluster(mapa_u32(bar_sfull(s2), 1));
+        if (++s2 == SCHED) { s2 = 0; ph2 ^= 1; }
+        if (v < 0) break;
+      }
+    }
+  } else if (warp == 0) {
+    // ================================ TMA producer (both CTAs: own halves) ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (;;) {
+        const int item = next_item(false);
+        if (item < 0) break;
+        int xt, zt;
+        if (!item_coords2(p, item, xt, zt)) continue;
+        for (int c = 0; c < p.nc; ++c)
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait_cl(bar_empty(stage), phase ^ 1, p.err, 1);
+            if (rank == 0) mbar_expect_tx(bar_full(stage), 2 * C::STAGE_BYTES);
+            const uint32_t full_leader = mapa_u32(bar_full(stage), 0);
+            const uint32_t sa = tiles + stage * C::STAGE_BYTES;
+            const int seg = kb / p.nkb, kk = (kb - seg * p.nkb) * BK;
+            tma_load_3d_2sm(sa, &tmA, full_leader, kk + (seg == 2 ? p.npad : 0), xt * 2 * BM + (int)rank * BM, c);
+            tma_load_3d_2sm(sa + BM * 128, &tmB, full_leader, kk + (seg == 1 ? p.npad : 0), zt * BN + (int)rank * (BN / 2), c);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int slot = 0; uint32_t sphase = 0;
+      for (;;) {
+        const int item = next_item(false);
+        if (item < 0) break;
+        int xt, zt;
+        if (!item_coords2(p, item, xt, zt)) continue;
+        for (int c = 0; c < p.nc; ++c) {
+          mbar_wait_cl(bar_tempty(slot), sphase ^ 1, p.err, 2);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + (uint32_t)(slot * BN);
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait_cl(bar_full(stage), phase, p.err, 3);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = tiles + stage * C::STAGE_BYTES;
+            const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + BM * 128);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              mma_tf32_2sm(tmem_d, adesc + (uint64_t)(k * UK * 4 / 16), bdesc + (uint64_t)(k * UK * 4 / 16), idesc,
+                           (kb | k) ? 1u : 0u);
+            mma_commit_2sm(bar_empty(stage), 3);                          // frees the stage in BOTH CTAs
+            if (kb == p.kblocks - 1) mma_commit_2sm(bar_tfull(slot), 3);    // accumulator complete in both TMEMs
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ column-record loader (both CTAs, all 256 columns) ================================
+    if (lane == 0) {
+      int b = 0; uint32_t bphase = 0;
+      for (;;) {
+        const int item = next_item(false);
+        if (item < 0) break;
+        int xt, zt;
+        if (!item_coords2(p, item, xt, zt)) continue;
+        for (int c = 0; c < p.nc; ++c) {
+          mbar_wait(bar_cempty(b), bphase ^ 1, p.err, 4);
+          mbar_expect_tx(bar_cfull(b), C::COL_BYTES);
+          bulk_load_1d(colbuf + b * C::COL_BYTES, p.colrec + ((size_t)c * p.nzp + (size_t)zt * BN) * RS, C::COL_BYTES,
+                       bar_cfull(b));
+          if (++b == 2) { b = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 4 .. 4+EW-1), rows of THIS CTA's 128 candidates ================================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int NCH = BN / 32 / (EW / 4);
+    const int row = q * 32 + lane;
+    int slot = 0; uint32_t sphase = 0;
+    int b = 0; uint32_t bphase = 0;
+    for (;;) {
+      const int item = next_item(true);
+      if (item < 0) break;
+      int xt, zt;
+      if (!item_coords2(p, item, xt, zt)) continue;
+      const long long xrow = (long long)xt * 2 * BM + (long long)rank * BM + row;
+      uint32_t bits[NCH];
+#pragma unroll
+      for (int h = 0; h < NCH; ++h) bits[h] = 0xffffffffu;
+      for (int c = 0; c < p.nc; ++c) {
+        float xx[4 * D4];
+        const float4* rr = reinterpret_cast<const float4*>(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
+#pragma unroll
+        for (int v = 0; v < D4; ++v) {
+          const float4 t = __ldg(rr + v);
+          xx[4 * v] = t.x; xx[4 * v + 1] = t.y; xx[4 * v + 2] = t.z; xx[4 * v + 3] = t.w;
+        }
+        const float4 rt = __ldg(rr + D4);
+        const float Cx = rt.x, ax = rt.y, bx = rt.z;
+        mbar_wait(bar_cfull(b), bphase, p.err, 5);
+        mbar_wait_cl(bar_tfull(slot), sphase, p.err, 6);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS) + (size_t)half * NCH * 32 * (RS / 4);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + half * NCH * 32);
+#pragma unroll
+        for (int h = 0; h < NCH; ++h) {
+          uint32_t r[32];
+          tmem_ld32(taddr + h * 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t w = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4* rec = cb + (size_t)(h * 32 + j) * (RS / 4);
+            const float4 tail4 = rec[D4];
+            float e = Cx - tail4.x;
+#pragma unroll
+            for (int v = 0; v < D4; ++v) {
+              const float4 zc4 = rec[v];
+              e = fmaf(xx[4 * v], zc4.x, e); e = fmaf(xx[4 * v + 1], zc4.y, e);
+              e = fmaf(xx[4 * v + 2], zc4.z, e); e = fmaf(xx[4 * v + 3], zc4.w, e);
+            }
+            const float cov = ex2_approx(e) - __uint_as_float(r[j]);
+            const float mu = fmaf(cov, ax, tail4.y);
+            const float t = fmaf(-(cov * cov), bx, tail4.z);
+            const bool ok = (mu >= 0.f) && (mu * mu >= t);
+            w |= ok ? (1u << j) : 0u;
+          }
+          bits[h] &= w;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_cluster(mapa_u32(bar_tempty(slot), 0)); mbar_arrive(bar_cempty(b)); }
+        if (++slot == SLOTS) { slot = 0; sphase ^= 1; }
+        if (++b == 2) { b = 0; bphase ^= 1; }
+      }
+      int cnt = 0;
+#pragma unroll
+      for (int h = 0; h < NCH; ++h) cnt += __popc(bits[h]);
+      if (xrow < p.nx && cnt) atomicAdd(p.counts + xrow, cnt);
+    }
+  }
+  // ---- teardown: neither CTA may exit (or free TMEM) while the other can still signal it
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP32 record builders.  h = log2(e)/2 so that  k_c(z,x) = exp2(Cx - Bz + sum_k xx_k z_k)
 //   row (candidate x):  xx_k = 2 h w_ck x_k ; Cx = log2 sf2_c - h sum_k w_ck x_k^2 ; a = beta*sigma/(sigma^2+sn2) ;
@@ -468,6 +792,38 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
   return SBO_OK;
 }
 
+template <int D4, int EW>
+static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
+                   const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err) {
+  using C = Cfg2<D4>;
+  CUtensorMap tmA, tmB;
+  const int rowlen = split ? 2 * fc.npad : fc.npad;
+  SBO_TRY(make_map(ctx, &tmA, Vx, rowlen, nxp, fc.nc, BM));
+  SBO_TRY(make_map(ctx, &tmB, Vz, rowlen, nzp, fc.nc, C::BN / 2));
+  Params p{};
+  p.nc = fc.nc; p.nkb = fc.npad / BK; p.kblocks = split ? 3 * p.nkb : p.nkb; p.npad = fc.npad; p.split = split;
+  p.nx = nx; p.nz = nz; p.nxp = nxp; p.nzp = nzp;
+  p.nxt = (int)cdiv(nx, 2 * BM); p.nzt = (int)cdiv(nz, C::BN);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int clusters = sms / 2;
+  // raster group: gx x tile pairs share each z tile; default keeps 4 z tiles in flight (as the 1-CTA kernel)
+  p.gx = ctx->opt_fantasy_gx > 0 ? (int)ctx->opt_fantasy_gx : (clusters + 3) / 4;
+  p.n_items = cdiv(p.nxt, p.gx) * p.gx * (long long)p.nzt;
+  SBO_REQUIRE(p.n_items < 2000000000LL, "too many tile pairs for one launch");
+  p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
+  p.sched_counter = (unsigned int*)(err + 1);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc2<D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = 2 * (int)((p.n_items < clusters) ? p.n_items : clusters);
+  k_fantasy_tc2<D4, EW><<<grid, 128 + 32 * EW, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
 }  // namespace tc
 
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
@@ -505,7 +861,11 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   ev_end(ctx);            // record prep = phase 6
   ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)
 #define TC_LAUNCH(BN_, D4_, EW_) SBO_TRY((tc::launch<BN_, D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)))
-  if (D4 == 1) {
+#define TC_LAUNCH2(D4_, EW_) SBO_TRY((tc::launch2<D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)))
+  if (variant & 4) {            // 2-CTA pairs (cta_group::2), BN = 256
+    if (D4 == 1) { if (variant & 2) TC_LAUNCH2(1, 8); else TC_LAUNCH2(1, 4); }
+    else         { if (variant & 2) TC_LAUNCH2(2, 8); else TC_LAUNCH2(2, 4); }
+  } else if (D4 == 1) {
     switch (variant & 3) {
       case 0: TC_LAUNCH(128, 1, 4); break;
       case 1: TC_LAUNCH(256, 1, 4); break;
@@ -520,6 +880,7 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
       default: TC_LAUNCH(256, 2, 8); break;
     }
   }
+#undef TC_LAUNCH2
 #undef TC_LAUNCH
   return SBO_OK;
 }

@@ -44,7 +44,8 @@ class GridEngine:
         if stream is not None:
             self._ck(self._lib.sbo_set_stream(self._h, C.c_void_p(int(stream))))
         import os
-        for env, opt in (("SBO_FANTASY_VARIANT", "fantasy_variant"), ("SBO_POSTERIOR_VARIANT", "posterior_variant")):
+        for env, opt in (("SBO_FANTASY_VARIANT", "fantasy_variant"), ("SBO_POSTERIOR_VARIANT", "posterior_variant"),
+                         ("SBO_FANTASY_GX", "fantasy_gx")):
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
 

@@ -494,7 +494,7 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5, 7])
 @pytest.mark.parametrize("name,n,beta,grid,rule", [("c1", 9, 3.0, [48, 40], "all"), ("c3", 20, 2.0, [45, 61], "any"),
                                                     ("c3", 35, 2.0, [70, 50], "all")])
 def test_fantasy_tensor_core_counts(engine, oracle, request, name, n, beta, grid, rule, variant, precision):
@@ -505,7 +505,7 @@ def test_fantasy_tensor_core_counts(engine, oracle, request, name, n, beta, grid
 
 
 @pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5, 7])
 def test_fantasy_tensor_core_synthetic(engine, oracle, variant, precision):
     from sbo_b200 import workloads
     for (d, ppd, n, G) in [(3, 14, 70, 3), (4, 9, 200, 4), (6, 5, 130, 3)]:
