@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--mode", default=os.environ.get("SBO_BENCH_MODE", "fantasy"))
     ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "tf32"))
+    ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end repetitions (default max(2, steps); the first is dropped when > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--prune", type=int, default=0, help="1: also time the step with the exact z-side pruning (extra key)")
@@ -238,11 +239,13 @@ def run_ours(args):
     fantasy = args.mode == "fantasy"
 
     def step(upload=True):
-        """One acquisition step on this rank's shard.  Multi-GPU: scalar all-reduces between the stages."""
-        if world == 1:
-            return eng.safeopt_step(ds, beta, mode=args.mode, precision=args.precision, upload=upload)
-        from sbo_b200 import sharded
-        return sharded.safeopt_step(eng, ds, beta, mode=args.mode, precision=args.precision, upload=upload)
+        """One acquisition step on this rank's shard.  Multi-GPU: collectives between the stages, issued on the
+        engine's stream (torch's current stream inside this context) so they are ordered with its kernels."""
+        with torch.cuda.stream(stream):
+            if world == 1:
+                return eng.safeopt_step(ds, beta, mode=args.mode, precision=args.precision, upload=upload)
+            from sbo_b200 import sharded
+            return sharded.safeopt_step(eng, ds, beta, mode=args.mode, precision=args.precision, upload=upload)
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
 
@@ -263,7 +266,7 @@ def run_ours(args):
     res = None
     for k in range(args.steps):
         flush.zero_()
-        torch.cuda.synchronize()
+        barrier()                      # ranks start every timed step together (no skew inside the event pair)
         with torch.cuda.stream(stream):
             ev[k][0].record(stream)
             res = step()
@@ -275,12 +278,13 @@ def run_ours(args):
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     # ---- end-to-end steps (host buffers in, host results out) ----
     t_e2e = []
-    for k in range(max(2, args.steps)):
+    for k in range(args.e2e_steps if args.e2e_steps else max(2, args.steps)):
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        r2 = step(upload=True)
-        safe = eng.mask(capi.MASK_SAFE)
+        with torch.cuda.stream(stream):          # the collectives must be ordered with the engine's kernels
+            r2 = step(upload=True)
+            safe = eng.mask(capi.MASK_SAFE)
         torch.cuda.synchronize()
         t_e2e.append(time.perf_counter() - t0)
     e2e_s = float(np.mean(t_e2e[1:])) if len(t_e2e) > 1 else t_e2e[0]
@@ -294,11 +298,16 @@ def run_ours(args):
     pruned = None
     if args.prune and fantasy:
         eng.set_option("fantasy_prune", 1)
-        step(); barrier()
+        with torch.cuda.stream(stream):
+            step()
+        barrier()
         tp = []
         for k in range(max(2, args.steps)):
             flush.zero_(); barrier()
-            t0 = time.perf_counter(); rp = step(); torch.cuda.synchronize(); tp.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            with torch.cuda.stream(stream):
+                rp = step()
+            torch.cuda.synchronize(); tp.append(time.perf_counter() - t0)
         eng.set_option("fantasy_prune", 0)
         pruned = {"ms_per_step": float(np.mean(tp)) * 1e3, "pairs_evaluated": int(rp["expander"]["pairs_evaluated"]),
                   "x_new_idx": int(rp["x_new_idx"]), "n_hit": int(rp["expander"]["n_hit"]),
@@ -349,7 +358,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": wl_name, "mode": args.mode, "precision": args.precision, "N": N, "n": n, "d": d, "G": G,
                        "beta": beta, "n_safe": int(res["n_safe"]), "n_unsafe": int(res["n_unsafe"]), "n_min": int(res["n_min"]),
-                       "pairs": pairs, "pairs_evaluated": int(ex["pairs_evaluated"]), "x_new_idx": int(res["x_new_idx"]),
+                       "pairs": pairs, "pairs_evaluated": int(ex["pairs_evaluated"]), "n_hit": int(ex["n_hit"]), "x_new_idx": int(res["x_new_idx"]),
                        "l2": "256 MiB flush buffer written between timed steps; working set >> L2",
                        "excludes": "plant evaluation and hyper-parameter fit (host side in the reference too)"},
             "phase_ms": ph, "clocks": clk, "gpu_launches": int(launches // max(1, args.steps)),

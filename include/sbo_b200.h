@@ -89,9 +89,11 @@ int sbo_get_model(sbo_ctx* ctx, double* L, double* W, double* alpha);
 int sbo_set_grid(sbo_ctx* ctx, int d, const int64_t* pts_per_dim, const double* lo, const double* hi);
 int sbo_set_points(sbo_ctx* ctx, int64_t N, int d, const double* pts);
 int sbo_set_shard(sbo_ctx* ctx, int64_t first, int64_t count);
-/* block-cyclic ownership (multi-GPU): rank r owns the blocks b = r, r+nranks, ... of `block` consecutive
- * grid points (block a multiple of 32), which balances |S| and |Z| across ranks.  Local point p maps to the
- * global index ((p / block) * nranks + rank) * block + p % block; *count = number of local points. */
+/* rotated block-cyclic ownership (multi-GPU): the grid is cut into blocks of `block` consecutive points (a
+ * multiple of 32); in super-block sb (nranks consecutive blocks) rank r owns slot (r + sb + sb/nranks +
+ * sb/nranks^2) % nranks, which balances |S| and |Z| across ranks even when the meshgrid axes are multiples of
+ * block*nranks.  Local point p (sb = p / block) maps to global index (sb*nranks + slot)*block + p % block;
+ * *count = number of local points. */
 int sbo_set_shard_cyclic(sbo_ctx* ctx, int rank, int nranks, int64_t block, int64_t* count);
 int sbo_point_coords(sbo_ctx* ctx, int64_t global_idx, double* x /* d */);
 
@@ -185,6 +187,11 @@ int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
  * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce */
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
+/* give device workspaces back to the driver (large grids: the V rows of the fantasy expander are n x count per
+ * constraint -- 51 GB per rank at C5).  what = 1: the per-point V rows kept by sbo_posterior(keep_v) (call after
+ * sbo_pairs_export_dev; a later fantasy prepare needs a new sbo_posterior); 2: the gathered pair operands
+ * (after sbo_pairs_finish_dev); 3: both.  No reference counterpart (the reference never materialises these). */
+int sbo_release(sbo_ctx* ctx, int what);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,7 @@ SIGNATURES = {
     "sbo_kernel_launches": (C.c_int64, [_P, C.c_int]),
     "sbo_phase_ms": (C.c_int, [_P, C.c_int, _D]),
     "sbo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "sbo_release": (C.c_int, [_P, C.c_int]),
 }
 
 _lib = None

@@ -206,7 +206,10 @@ int sbo_set_shard_cyclic(sbo_ctx* ctx, int rank, int nranks, int64_t block, int6
   GridSpec& g = ctx->gs;
   const long long nblk = cdiv(g.N, block);
   long long count = 0;
-  for (long long b = rank; b < nblk; b += nranks) count += (b == nblk - 1) ? (g.N - b * block) : block;
+  for (long long sb = 0; sb * nranks < nblk; ++sb) {      // same slot rule as shard_global()
+    const long long b = sb * nranks + (rank + sb + sb / nranks + sb / ((long long)nranks * nranks)) % nranks;
+    if (b < nblk) count += (b == nblk - 1) ? (g.N - b * block) : block;
+  }
   SBO_REQUIRE(count >= 1, "this rank owns no grid points");
   g.first = 0; g.count = count;
   g.cyc_n = nranks; g.cyc_rank = rank; g.cyc_blk = block;
@@ -372,6 +375,17 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms) {
   ENTER();
   SBO_REQUIRE(phase >= 0 && phase < 8 && ms, "bad phase");
   *ms = ctx->phase_ms[phase];
+  return SBO_OK;
+}
+
+int sbo_release(sbo_ctx* ctx, int what) {
+  ENTER();
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (what & 1) { free_buf(ctx->vall); ctx->keep_v = 0; }
+  if (what & 2) {
+    for (DevBuf* b : {&ctx->vx, &ctx->vz, &ctx->exp_v, &ctx->tc_row, &ctx->tc_col, &ctx->imp_rows}) free_buf(*b);
+    ctx->ps = PairStage{};
+  }
   return SBO_OK;
 }
 

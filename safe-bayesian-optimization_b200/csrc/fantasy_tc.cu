@@ -854,10 +854,11 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
     SBO_LAUNCH_CHECK();
   }
   int* err = (int*)ctx->tc_err.p;
-  // variant: bit 0: BN = 256, bit 1: 8 epilogue warps; < 0 = auto: BN = 256 (less operand traffic); 8 epilogue warps
-  // when the epilogue outweighs the MMAs (short K) or carries 12-float records (d > 4)
+  // variant: bit 0: BN = 256, bit 1: 8 epilogue warps, bit 2: 2-CTA pairs (cta_group::2, 256 x 256 tile pairs);
+  // < 0 = auto: 2-CTA pairs (a third less L2->SM operand traffic, 6 stages); 8 epilogue warps when the epilogue
+  // outweighs the MMAs (short K) or carries 12-float records (d > 4)
   int variant = (int)ctx->opt_fantasy_variant;
-  if (variant < 0) variant = 1 | ((fc.npad <= 256 || D4 == 2) ? 2 : 0);
+  if (variant < 0) variant = 5 | ((fc.npad <= 256 || D4 == 2) ? 2 : 0);
   ev_end(ctx);            // record prep = phase 6
   ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)
 #define TC_LAUNCH(BN_, D4_, EW_) SBO_TRY((tc::launch<BN_, D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)))

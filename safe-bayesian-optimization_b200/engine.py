@@ -41,8 +41,10 @@ class GridEngine:
         self.first = 0
         self.count = 0
         self.grid_kind = None
+        self.stream = None                  # the raw cudaStream_t the context launches on (None = its own stream)
         if stream is not None:
             self._ck(self._lib.sbo_set_stream(self._h, C.c_void_p(int(stream))))
+            self.stream = int(stream)
         import os
         for env, opt in (("SBO_FANTASY_VARIANT", "fantasy_variant"), ("SBO_POSTERIOR_VARIANT", "posterior_variant"),
                          ("SBO_FANTASY_GX", "fantasy_gx")):
@@ -70,6 +72,10 @@ class GridEngine:
 
     def set_option(self, name, value):
         self._ck(self._lib.sbo_set_option(self._h, name.encode(), int(value)))
+
+    def release(self, what=3):
+        """Free device workspaces: 1 = per-point V rows, 2 = gathered pair operands, 3 = both (large grids)."""
+        self._ck(self._lib.sbo_release(self._h, int(what)))
 
     def kernel_launches(self, reset=False):
         return int(self._lib.sbo_kernel_launches(self._h, 1 if reset else 0))

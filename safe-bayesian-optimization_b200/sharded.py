@@ -4,8 +4,9 @@ this module only inserts the collectives (``torch.distributed``: NCCL on GPUs, g
 
   all-reduce-min  (min_S ucb_0, index) and (min_S lcb_0, index)      between the two set passes
   all-reduce-max  Lipschitz constants, (max_M var_0, index)
-  all-gather      the candidates' rows (+ V rows in fantasy mode): every rank pairs ALL candidates x in S
-                  with ITS OWN unsafe points z
+  broadcasts      the candidates' rows (+ V rows in fantasy mode), one block per rank straight into the gathered
+                  buffer (an all-gather with uneven blocks): every rank pairs ALL candidates x in S with ITS OWN
+                  unsafe points z
   all-reduce      per-candidate hit flags (max) / newly-safe counts (sum)
   all-gather      local optima (value, global index) -> deterministic reduction, lowest index on ties
 
@@ -27,6 +28,16 @@ from . import _capi as capi
 def _sync(device):
     if device.type == "cuda":
         torch.cuda.synchronize(device)
+
+
+def _order(eng, device):
+    """Order the engine's kernels with torch's collectives: nothing to do when both use the same CUDA stream
+    (bench.py runs the step inside torch.cuda.stream(engine stream)), else a device synchronise."""
+    if device.type != "cuda":
+        return
+    if getattr(eng, "stream", None) is not None and eng.stream == torch.cuda.current_stream(device).cuda_stream:
+        return
+    torch.cuda.synchronize(device)
 
 
 def gather_scalars(values, device, group=None):
@@ -59,22 +70,40 @@ def reduce_arg(pairs, device, maximize=False, group=None):
     return out
 
 
-def all_gather_rows(local, n_all, group=None):
-    """Concatenate per-rank row blocks of different lengths: local (n_r, w) -> (sum n_r, w)."""
-    world = len(n_all)
-    nmax = int(max(n_all))
-    w = local.shape[1]
-    if nmax == 0:
-        return local.new_empty((0, w))
-    pad = local.new_zeros((nmax, w))
-    pad[: local.shape[0]] = local
-    out = local.new_empty(world * nmax * w)
-    dist.all_gather_into_tensor(out, pad.view(-1), group=group)
-    out = out.view(world * nmax, w)
-    del pad
-    if all(int(n) == nmax for n in n_all):
-        return out
-    return torch.cat([out[r * nmax: r * nmax + int(n_all[r])] for r in range(world)], dim=0)
+def exchange_rows(buf, n_all, group=None):
+    """buf (sum n_r, w) already holds THIS rank's rows at its offset; fill in every other rank's block in place.
+    One broadcast per non-empty rank straight into the destination slice: no padding, no concatenation copy
+    (the V rows are 41 GB at C5), and uneven block sizes cost nothing."""
+    off = 0
+    for r, n in enumerate(n_all):
+        n = int(n)
+        if n:
+            dist.broadcast(buf[off: off + n], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        off += n
+    return buf
+
+
+class _Trace:
+    """SBO_SHARDED_TRACE=1: rank 0 prints the wall time of every stage (device-synchronised) -- diagnosis only."""
+
+    def __init__(self, device):
+        import os
+        self.on = os.environ.get("SBO_SHARDED_TRACE") == "1"
+        self.device, self.t, self.rows = device, None, []
+
+    def mark(self, name):
+        if not self.on:
+            return
+        import time
+        _sync(self.device)
+        now = time.perf_counter()
+        if self.t is not None:
+            self.rows.append((name, (now - self.t) * 1e3))
+        self.t = now
+
+    def dump(self):
+        if self.on and dist.get_rank() == 0:
+            print("sharded trace (ms): " + "  ".join(f"{n}={t:.2f}" for n, t in self.rows), flush=True)
 
 
 def first_best(per_value, per_idx, maximize):
@@ -110,22 +139,44 @@ def _posterior_and_sets(eng, ds, beta, unsafe_rule, with_grad, keep_v, upload, d
     return out
 
 
+BIG_V_BYTES = 4 << 30      # above this the per-point V rows and the gathered copies are released as soon as possible
+
+
 def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
-    """prepare -> export -> all-gather -> import -> run -> all-reduce -> finish -> reduce the local optima."""
+    """prepare -> export into the gathered buffer -> broadcast blocks -> import -> run -> all-reduce -> finish ->
+    reduce the local optima."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    tr = _Trace(device)
+    tr.mark("start")
     info = eng.pairs_prepare(mode, prec, beta, L)
     nx, nz = int(info["n_x_local"]), int(info["n_z_local"])
     n_all = gather_scalars([nx], device, group)[:, 0].astype(np.int64)
     n_total, offset = int(n_all.sum()), int(n_all[:rank].sum())
-    rows = torch.empty((max(nx, 1), int(info["row_doubles"])), dtype=torch.float64, device=device)
+    tr.mark("prepare")
     vrow = int(info["vrow_bytes"])
-    vrows = torch.empty((max(nx, 1), max(vrow, 1)), dtype=torch.uint8, device=device) if vrow else None
-    eng.pairs_export(rows, vrows)
-    rows_all = all_gather_rows(rows[:nx], n_all, group)
-    v_all = all_gather_rows(vrows[:nx], n_all, group) if vrow else None
-    del rows, vrows
-    _sync(device)
+    big = vrow * n_total > BIG_V_BYTES
+    rows_all = torch.empty((max(n_total, 1), int(info["row_doubles"])), dtype=torch.float64, device=device)
+    v_all = torch.empty((max(n_total, 1), max(vrow, 1)), dtype=torch.uint8, device=device) if vrow else None
+    # every rank writes its candidates' rows straight into its slice of the gathered buffers
+    eng.pairs_export(rows_all[offset: offset + max(nx, 1)] if nx else rows_all,
+                     (v_all[offset: offset + max(nx, 1)] if nx else v_all) if vrow else None)
+    if big and hasattr(eng, "release"):
+        eng.release(1)                       # the per-point V rows are not needed after the export
+    tr.mark("export")
+    _order(eng, device)
+    exchange_rows(rows_all, n_all, group)
+    if vrow:
+        exchange_rows(v_all, n_all, group)
+    tr.mark("exchange")
+    _order(eng, device)
     eng.pairs_import(n_total, rows_all, v_all)
+    if big:
+        _sync(device)
+        del v_all
+        v_all = None
+        if device.type == "cuda":
+            torch.cuda.empty_cache()         # hand the gathered copy back before the GEMM workspaces are sized
+    tr.mark("import")
     nc = eng.G - 1
     fantasy = mode == capi.MODE_FANTASY
     if goose:
@@ -134,17 +185,24 @@ def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
         result = torch.zeros(max(n_total, 1), dtype=torch.int32, device=device)
     else:
         result = torch.zeros(max(nc * n_total, 1), dtype=torch.uint8, device=device)
-    _sync(device)
+    _order(eng, device)
     eng.pairs_run(goose, result)
+    tr.mark("run")
+    _order(eng, device)
     if not goose and n_total > 0:          # x is global: combine the verdicts of all z shards
         dist.all_reduce(result, op=dist.ReduceOp.SUM if fantasy else dist.ReduceOp.MAX, group=group)
-    _sync(device)
+    tr.mark("allreduce")
+    _order(eng, device)
     loc = eng.pairs_finish(goose, 0 if goose else offset, result, want_counts=want_counts)
     nmask = 1 if fantasy else nc
     red = reduce_arg([(loc["per_value"][c], loc["per_idx"][c]) for c in range(nmask)], device, not goose, group) if nmask else []
     per_value, per_idx = [v for v, _ in red], [i for _, i in red]
     bi, bv = first_best(per_value, per_idx, maximize=not goose)
     tot = gather_scalars([nz, loc["n_hit"], loc["pairs_evaluated"]], device, group).sum(axis=0)
+    if big and hasattr(eng, "release"):
+        eng.release(2)                       # gathered operands: the next step's V rows need the room
+    tr.mark("finish")
+    tr.dump()
     out = {"best_idx": bi, "best_value": bv, "per_idx": per_idx, "per_value": per_value, "n_x": n_total,
            "n_z": int(tot[0]), "n_hit": int(tot[1]), "pairs_evaluated": int(tot[2]),
            "pairs_algorithmic": n_total * int(tot[0]) * nc, "local": loc}

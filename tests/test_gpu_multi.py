@@ -28,6 +28,6 @@ def test_two_gpus_agree_with_one(mode, precision):
     one = _run([sys.executable, "bench.py"] + common)
     two = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                 "--master-addr", "127.0.0.1", "--master-port", "29533", "bench.py", "--gpus", "2"] + common)
-    for k in ["n_safe", "n_unsafe", "n_min", "pairs", "x_new_idx"]:
+    for k in ["n_safe", "n_unsafe", "n_min", "pairs", "n_hit", "x_new_idx"]:
         assert one["config"][k] == two["config"][k], k
     assert two["n_gpus"] == 2

@@ -431,6 +431,37 @@ def test_c4_full_size_properties(engine, oracle):
     assert np.max(np.abs(mt - Yraw) / ds["Y_std"]) < 0.2 and np.max(vt / ds["Y_std"] ** 2) < 0.05
 
 
+@pytest.mark.parametrize("world,block", [(2, 32), (3, 64), (8, 32), (8, 256)])
+def test_rotated_block_cyclic_shards_tile_the_grid(engine, oracle, c3, world, block):
+    """sbo_set_shard_cyclic: the ranks' shards are disjoint, cover the grid, and local point p is the global point
+    the header documents (posterior of the shard == rows of the full-grid posterior)."""
+    ds = golden_ds(oracle, c3, 20)
+    engine.set_model(ds)
+    grid = [50, 37]                                    # 1850 points: ragged last block, partial last super-block
+    engine.set_grid(c3["lo"], c3["hi"], grid)
+    m_full, v_full = engine.posterior()
+    N = m_full.shape[0]
+    nblk = (N + block - 1) // block
+    seen = np.zeros(N, dtype=int)
+    for rank in range(world):
+        sb = np.arange((nblk + world - 1) // world)
+        gb = sb * world + (rank + sb + sb // world + sb // (world * world)) % world
+        gb = gb[gb < nblk]
+        gidx = np.concatenate([np.arange(b * block, min(N, (b + 1) * block)) for b in gb])
+        cnt = engine.set_shard_cyclic(rank, world, block)
+        assert cnt == gidx.size
+        m, v = engine.posterior()
+        np.testing.assert_array_equal(m, m_full[gidx])
+        np.testing.assert_array_equal(v, v_full[gidx])
+        seen[gidx] += 1
+        # arg-reductions report GLOBAL indices
+        s = engine.sets_pass1(2.0, 0)
+        if s["min_lcb0_idx"] >= 0:
+            assert s["min_lcb0_idx"] in set(gidx.tolist())
+    assert (seen == 1).all()
+    engine.set_grid(c3["lo"], c3["hi"], grid)           # back to the unsharded default
+
+
 # ------------------------------------------------------------------------------------------------
 # fantasy expander, TF32 tcgen05/TMEM kernel.  Three checks, tolerances stated on the FP64 margin
 #   m(z,x) = min_i (mu'_i - beta*sigma'_i)   (normalised units)  of a (z,x) pair:

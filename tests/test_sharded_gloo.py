@@ -25,8 +25,10 @@ class OracleEngine:
         self.O, self.rank, self.world = O, rank, world
         self.points_all = O.make_grid(lo, hi, pts)
         N = self.points_all.shape[0]
-        blocks = np.arange((N + block - 1) // block)
-        mine = blocks[blocks % world == rank]
+        nblk = (N + block - 1) // block
+        sb = np.arange((nblk + world - 1) // world)            # rotated block-cyclic, as sbo_set_shard_cyclic
+        mine = sb * world + (rank + sb + sb // world + sb // (world * world)) % world
+        mine = mine[mine < nblk]
         self.gidx = np.concatenate([np.arange(b * block, min(N, (b + 1) * block)) for b in mine])
         self.points = self.points_all[self.gidx]
         self.device = 0
