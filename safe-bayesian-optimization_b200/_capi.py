@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsbo_b200.so")
+# SBO_B200_LIB: developer override to A/B-test another build of the same library (never a different backend)
+LIB_PATH = os.environ.get("SBO_B200_LIB") or os.path.join(_HERE, "libsbo_b200.so")
 
 MAX_D, MAX_G = 8, 8
 UNSAFE_ALL, UNSAFE_ANY = 0, 1

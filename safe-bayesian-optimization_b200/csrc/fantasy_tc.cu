@@ -122,6 +122,88 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// ---- packed FP32 (FFMA2 / FMUL2 / FADD2 on sm_100a): two z columns per instruction in the epilogue ----
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// w |= bit  iff  mu >= 0 and mu^2 >= t   (two FSETP chained through the predicate + one predicated LOP3)
+__device__ __forceinline__ void set_bit_if_safe(uint32_t& w, float mu, float mm, float t, uint32_t bit) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ge.f32 p, %1, 0f00000000;\n\t"
+      "setp.ge.and.f32 p, %2, %3, p;\n\t"
+      "@p or.b32 %0, %0, %4;\n\t}"
+      : "+r"(w)
+      : "f"(mu), "f"(mm), "f"(t), "r"(bit));
+}
+
+// row constants of one candidate for one constraint, duplicated into both halves of a packed pair
+template <int D4>
+struct RowConsts {
+  uint64_t xx[4 * D4], Cx, ax, nbx;
+  __device__ __forceinline__ void load(const float* __restrict__ rowrec_row) {
+    const float4* rr = reinterpret_cast<const float4*>(rowrec_row);
+#pragma unroll
+    for (int v = 0; v < D4; ++v) {
+      const float4 t = __ldg(rr + v);
+      xx[4 * v] = pk2(t.x, t.x); xx[4 * v + 1] = pk2(t.y, t.y); xx[4 * v + 2] = pk2(t.z, t.z); xx[4 * v + 3] = pk2(t.w, t.w);
+    }
+    const float4 rt = __ldg(rr + D4);
+    Cx = pk2(rt.x, rt.x); ax = pk2(rt.y, rt.y); nbx = pk2(-rt.z, -rt.z);
+  }
+};
+
+// One 32-column chunk of the fused epilogue for one candidate row: acc[32] = v_x . v_z from TMEM, `rec` = the 16
+// pair-interleaved column records of the chunk in shared memory ((4*D4+4) float2 per column pair:
+// z_k pairs, -Bz pair, m_z pair, s'_z pair, pad).  Same operations in the same order as the scalar form
+// (e = (Cx - Bz) + sum xx_k z_k; cov = exp2(e) - acc; mu = cov*a + m; t = s' - cov^2 b'), two columns per FFMA2.
+template <int D4>
+__device__ __forceinline__ uint32_t epilogue_chunk(const uint32_t (&acc)[32], const uint64_t* __restrict__ rec, const RowConsts<D4>& rc) {
+  constexpr int RS = 4 * D4 + 4;
+  const uint64_t minus1 = pk2(-1.f, -1.f);
+  uint32_t w = 0;
+#pragma unroll
+  for (int jp = 0; jp < 16; ++jp) {
+    const uint64_t* p = rec + jp * RS;
+    uint64_t e = add2(rc.Cx, p[4 * D4]);
+#pragma unroll
+    for (int k = 0; k < 4 * D4; ++k) e = fma2(rc.xx[k], p[k], e);
+    float e0, e1;
+    upk2(e, e0, e1);
+    const uint64_t ex = pk2(ex2_approx(e0), ex2_approx(e1));
+    const uint64_t a2 = pk2(__uint_as_float(acc[2 * jp]), __uint_as_float(acc[2 * jp + 1]));
+    const uint64_t cov = fma2(a2, minus1, ex);
+    const uint64_t mu = fma2(cov, rc.ax, p[4 * D4 + 1]);
+    const uint64_t t = fma2(mul2(cov, cov), rc.nbx, p[4 * D4 + 2]);
+    const uint64_t mm = mul2(mu, mu);
+    float mu0, mu1, t0, t1, m0, m1;
+    upk2(mu, mu0, mu1); upk2(t, t0, t1); upk2(mm, m0, m1);
+    set_bit_if_safe(w, mu0, m0, t0, 1u << (2 * jp));
+    set_bit_if_safe(w, mu1, m1, t1, 2u << (2 * jp));
+  }
+  return w;
+}
+
 // work item = one (x tile, z tile) pair, all constraints.  Items are ordered so that a group of GX x tiles sweeps
 // the z tiles together: the GX*768 KB of x operands stay L2-resident while each z tile is reused by GX consecutive
 // items.  Items are handed out dynamically (atomic counter -> smem ring), which bounds the drift between CTAs to
@@ -313,44 +395,20 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int h = 0; h < NCH; ++h) bits[h] = 0xffffffffu;
       for (int c = 0; c < p.nc; ++c) {
         // row record of this candidate for constraint c: xx[4*D4], Cx, a, b', pad
-        float xx[4 * D4];
-        const float4* rr = reinterpret_cast<const float4*>(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
-#pragma unroll
-        for (int v = 0; v < D4; ++v) {
-          const float4 t = __ldg(rr + v);
-          xx[4 * v] = t.x; xx[4 * v + 1] = t.y; xx[4 * v + 2] = t.z; xx[4 * v + 3] = t.w;
-        }
-        const float4 rt = __ldg(rr + D4);
-        const float Cx = rt.x, ax = rt.y, bx = rt.z;
+        RowConsts<D4> rc;
+        rc.load(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
         mbar_wait(bar_cfull(b), bphase, p.err, 5);
         mbar_wait(bar_tfull(slot), sphase, p.err, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS) + (size_t)half * NCH * 32 * (RS / 4);
+        // pair-interleaved column records: RS packed pairs per two columns
+        const uint64_t* cb = reinterpret_cast<const uint64_t*>(colbuf_ptr + (size_t)b * BN * RS) + (size_t)half * NCH * 16 * RS;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + half * NCH * 32);
 #pragma unroll
         for (int h = 0; h < NCH; ++h) {
           uint32_t r[32];
           tmem_ld32(taddr + h * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          uint32_t w = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4* rec = cb + (size_t)(h * 32 + j) * (RS / 4);
-            const float4 tail4 = rec[D4];                     // Bz, m_z, s'_z, pad
-            float e = Cx - tail4.x;
-#pragma unroll
-            for (int v = 0; v < D4; ++v) {
-              const float4 zc4 = rec[v];
-              e = fmaf(xx[4 * v], zc4.x, e); e = fmaf(xx[4 * v + 1], zc4.y, e);
-              e = fmaf(xx[4 * v + 2], zc4.z, e); e = fmaf(xx[4 * v + 3], zc4.w, e);
-            }
-            const float cov = ex2_approx(e) - __uint_as_float(r[j]);
-            const float mu = fmaf(cov, ax, tail4.y);
-            const float t = fmaf(-(cov * cov), bx, tail4.z);
-            const bool ok = (mu >= 0.f) && (mu * mu >= t);
-            w |= ok ? (1u << j) : 0u;
-          }
-          bits[h] &= w;
+          bits[h] &= epilogue_chunk<D4>(r, cb + (size_t)h * 16 * RS, rc);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -635,44 +693,20 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
       for (int h = 0; h < NCH; ++h) bits[h] = 0xffffffffu;
       for (int c = 0; c < p.nc; ++c) {
-        float xx[4 * D4];
-        const float4* rr = reinterpret_cast<const float4*>(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
-#pragma unroll
-        for (int v = 0; v < D4; ++v) {
-          const float4 t = __ldg(rr + v);
-          xx[4 * v] = t.x; xx[4 * v + 1] = t.y; xx[4 * v + 2] = t.z; xx[4 * v + 3] = t.w;
-        }
-        const float4 rt = __ldg(rr + D4);
-        const float Cx = rt.x, ax = rt.y, bx = rt.z;
+        RowConsts<D4> rc;
+        rc.load(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
         mbar_wait(bar_cfull(b), bphase, p.err, 5);
         mbar_wait_cl(bar_tfull(slot), sphase, p.err, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const float4* cb = reinterpret_cast<const float4*>(colbuf_ptr + (size_t)b * BN * RS) + (size_t)half * NCH * 32 * (RS / 4);
+        // pair-interleaved column records: RS packed pairs per two columns
+        const uint64_t* cb = reinterpret_cast<const uint64_t*>(colbuf_ptr + (size_t)b * BN * RS) + (size_t)half * NCH * 16 * RS;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + half * NCH * 32);
 #pragma unroll
         for (int h = 0; h < NCH; ++h) {
           uint32_t r[32];
           tmem_ld32(taddr + h * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          uint32_t w = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4* rec = cb + (size_t)(h * 32 + j) * (RS / 4);
-            const float4 tail4 = rec[D4];
-            float e = Cx - tail4.x;
-#pragma unroll
-            for (int v = 0; v < D4; ++v) {
-              const float4 zc4 = rec[v];
-              e = fmaf(xx[4 * v], zc4.x, e); e = fmaf(xx[4 * v + 1], zc4.y, e);
-              e = fmaf(xx[4 * v + 2], zc4.z, e); e = fmaf(xx[4 * v + 3], zc4.w, e);
-            }
-            const float cov = ex2_approx(e) - __uint_as_float(r[j]);
-            const float mu = fmaf(cov, ax, tail4.y);
-            const float t = fmaf(-(cov * cov), bx, tail4.z);
-            const bool ok = (mu >= 0.f) && (mu * mu >= t);
-            w |= ok ? (1u << j) : 0u;
-          }
-          bits[h] &= w;
+          bits[h] &= epilogue_chunk<D4>(r, cb + (size_t)h * 16 * RS, rc);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -700,7 +734,8 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // FP32 record builders.  h = log2(e)/2 so that  k_c(z,x) = exp2(Cx - Bz + sum_k xx_k z_k)
 //   row (candidate x):  xx_k = 2 h w_ck x_k ; Cx = log2 sf2_c - h sum_k w_ck x_k^2 ; a = beta*sigma/(sigma^2+sn2) ;
 //                       b' = beta^2/(sigma^2+sn2)
-//   col (unsafe z):     z_k ; Bz = h sum_k w_ck z_k^2 ; m_z = mean/Ystd ; s'_z = beta^2 var/Ystd^2
+//   col (unsafe z):     z_k ; -Bz, Bz = h sum_k w_ck z_k^2 ; m_z = mean/Ystd ; s'_z = beta^2 var/Ystd^2
+//                       (stored pair-interleaved: two adjacent columns form packed f32x2 operands)
 // ---------------------------------------------------------------------------------------------
 template <int D4>
 __global__ void __launch_bounds__(256)
@@ -710,10 +745,13 @@ k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, cons
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (t >= npadrows) return;
-  float* o = rec + ((size_t)c * npadrows + t) * RS;
+  // rows: RS floats per candidate.  columns: pair-interleaved, entry k of column t at pair(t/2)*2*RS + 2*k + (t&1),
+  // so that the epilogue reads (column 2p, column 2p+1) as one packed f32x2 operand
+  float* o = is_row ? rec + ((size_t)c * npadrows + t) * RS : rec + ((size_t)c * npadrows + (t & ~1LL)) * RS + (t & 1);
+  const int st = is_row ? 1 : 2;
   if (t >= n) {
-    for (int k = 0; k < RS; ++k) o[k] = 0.f;
-    if (!is_row) o[4 * D4 + 1] = -1e30f;         // padded z columns can never become safe
+    for (int k = 0; k < RS; ++k) o[k * st] = 0.f;
+    if (!is_row) o[(4 * D4 + 1) * st] = -1e30f;         // padded z columns can never become safe
     return;
   }
   const double h = 0.5 * 1.4426950408889634;
@@ -722,7 +760,7 @@ k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, cons
     const double x = (k < fc.d) ? coords[(size_t)k * n + t] : 0.0;
     const double w = (k < fc.d) ? fc.inv_ell[c][k] : 0.0;
     q += w * x * x;
-    o[k] = is_row ? (float)(2.0 * h * w * x) : (float)x;
+    o[k * st] = is_row ? (float)(2.0 * h * w * x) : (float)x;
   }
   const double av = a[(size_t)c * n + t], bv = b[(size_t)c * n + t];
   if (is_row) {
@@ -730,11 +768,11 @@ k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, cons
     o[4 * D4 + 1] = (float)av;
     o[4 * D4 + 2] = (float)(fc.beta * fc.beta * bv);
   } else {
-    o[4 * D4] = (float)(h * q);
-    o[4 * D4 + 1] = (float)av;
-    o[4 * D4 + 2] = (float)(fc.beta * fc.beta * bv);
+    o[(4 * D4) * st] = -(float)(h * q);                  // stored negated: e = (Cx + (-Bz)) + ...
+    o[(4 * D4 + 1) * st] = (float)av;
+    o[(4 * D4 + 2) * st] = (float)(fc.beta * fc.beta * bv);
   }
-  o[4 * D4 + 3] = 0.f;
+  o[(4 * D4 + 3) * st] = 0.f;
 }
 
 static int make_map(sbo_ctx* ctx, CUtensorMap* map, const float* base, int rowlen, long long rows, int nc, int box_rows) {
