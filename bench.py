@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end repetitions (default max(2, steps); the first is dropped when > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
+    ap.add_argument("--no-reference-configs", action="store_true", help="skip the C1-C3 step times (extra key)")
     ap.add_argument("--prune", type=int, default=0, help="1: also time the step with the exact z-side pruning (extra key)")
     return ap.parse_args()
 
@@ -184,11 +185,58 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------
+# BASELINE.json configs[0..2]: the reference's own problems on its 400x400 grid (step time part of the metric)
+# --------------------------------------------------------------------------------------------
+# wall seconds of the reference's own Minimizer()+Expander() / minimize_obj_lcb()+Target()+explore_safeset() DE runs
+# for these model states, recorded when tests/golden/make_reference_vectors.py ran the reference's unmodified source
+# (NumPy stand-in for JAX, 1 host core, build container) -- context only, not measured in this run
+REF_DE_SECONDS = {"C1 SafeOpt/Benoit n=14": 9.3, "C2 GoOSE/Benoit n=14": 13.1, "C3 SafeOpt/WOR n=35": 53.1}
+
+
+def reference_configs(eng, torch, reps=5):
+    """Step time (host wall clock around a device sync, model upload included) of one SafeOpt / GoOSE acquisition
+    step in the reference-exact Lipschitz mode on the reference's 400x400 grid, for the model states the
+    reference's own source produced (tests/golden/ref_*.npz)."""
+    out = {}
+    gdir = os.path.join(ROOT, "tests", "golden")
+    cases = [("C1 SafeOpt/Benoit n=14", "ref_c1_benoit.npz", 14, "safeopt"),
+             ("C2 GoOSE/Benoit n=14", "ref_c1_benoit.npz", 14, "goose"),
+             ("C3 SafeOpt/WOR n=35", "ref_c3_wor.npz", 35, "safeopt")]
+    for name, f, n, kind in cases:
+        try:
+            r = np.load(os.path.join(gdir, f))
+            ds = {k: r[f"{k}_{n}"] for k in ("X_mean", "X_std", "Y_mean", "Y_std", "X_norm", "Y_norm", "hypopt")}
+            beta = float(r["beta"])
+            eng.set_grid(r["bound"][:, 0], r["bound"][:, 1], [400, 400])
+            step = (lambda: eng.safeopt_step(ds, beta)) if kind == "safeopt" else (lambda: eng.goose_step(ds, beta))
+            st = step()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                st = step()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            pr = st["expander"] if kind == "safeopt" else st["target"]
+            out[name] = {"ms_per_step": float(np.median(ts)) * 1e3, "grid": "400x400", "mode": "lipschitz", "G": int(ds["Y_norm"].shape[1]),
+                         "n_safe": int(st["n_safe"]), "n_unsafe": int(st["n_unsafe"]), "pairs": int(pr["pairs_algorithmic"]),
+                         "pairs_evaluated": int(pr["pairs_evaluated"]), "x_new_idx": int(st["x_new_idx"]),
+                         "reference_de_seconds_recorded": REF_DE_SECONDS[name]}
+        except Exception as e:  # pragma: no cover
+            out[name] = {"error": str(e)}
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of k_fantasy_tc per launch from the committed ncu capture
 # (profiles/): filled in when a capture of the same configuration exists, else null
-TRAFFIC_NCU = {}
+TRAFFIC_NCU = {
+    # profiles/r01_ncu_fantasy_tc2_summary.txt: k_fantasy_tc2<1,4> on C4/TF32, one launch = the whole pair stage:
+    # 123.59 GB read + 0.03 GB written (z tiles are re-read once per x raster group; 4 % of HBM bandwidth)
+    ("c4", "tf32"): 123.59e9 + 0.0285e9,
+}
 
 
 def measure_peaks(torch, dev):
@@ -367,6 +415,8 @@ def run_ours(args):
             "roofline": roof, "peaks": {**peaks, "hbm_gbs": mp.get("hbm_gbs"), "bf16_tflops": mp.get("bf16_tflops")}}
     if pruned is not None:
         line["pruned"] = pruned
+    if world == 1 and not args.no_reference_configs:
+        line["reference_configs"] = reference_configs(eng, torch)
     if not args.no_cpu_baseline and world == 1:
         s = cpu_sample_step(ds, lo, hi, pts, beta, args.mode)
         t_full = cpu_extrapolate(s, N, pairs)
