@@ -89,7 +89,7 @@ int sbo_destroy(sbo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->Xn, &ctx->Yn, &ctx->alpha, &ctx->W, &ctx->Kmat, &ctx->info, &ctx->pts, &ctx->mean, &ctx->var,
-                    &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
+                    &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->tile_bb, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
                     &ctx->m_tgt, &ctx->partials, &ctx->result, &ctx->scan_a, &ctx->scan_b, &ctx->xs_idx, &ctx->zs_idx,
                     &ctx->xs_pay, &ctx->zs_pay, &ctx->hits, &ctx->counts, &ctx->pairctr, &ctx->imp_rows, &ctx->vx, &ctx->vz,
                     &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v, &ctx->m_prune})
@@ -394,6 +394,7 @@ int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value) {
   SBO_REQUIRE(name != nullptr, "null option name");
   if (!strcmp(name, "posterior_variant")) { ctx->opt_posterior_variant = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_variant")) { ctx->opt_fantasy_variant = value; return SBO_OK; }
+  if (!strcmp(name, "pair_cull")) { ctx->opt_pair_cull = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_gx")) { ctx->opt_fantasy_gx = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_prune")) { ctx->opt_fantasy_prune = value; return SBO_OK; }
   return sbo_fail(ctx, SBO_ERR_INVALID, std::string("unknown option ") + name);

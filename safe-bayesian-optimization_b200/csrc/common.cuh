@@ -146,6 +146,7 @@ struct sbo_ctx {
   DevBuf vx, vz, aux_x, aux_z;
   DevBuf pp_x, pp_m, pp_v, pp_k, pp_g;   // scratch of the arbitrary-point posterior calls
   DevBuf tc_row, tc_col, tc_err;          // FP32 row/column records of the tcgen05 fantasy kernel
+  DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
   PairStage ps;
   // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
@@ -160,6 +161,7 @@ struct sbo_ctx {
   DevBuf m_prune;
   int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps;
                                      // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
+  int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles
   int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };
 

@@ -33,6 +33,66 @@ __device__ __forceinline__ bool reach_test(double s, double r2, double u, double
 }
 
 // ---------------------------------------------------------------------------------------------
+// Exact tile culling.  bb = [lo[D][ntiles] | hi[D][ntiles] | r2max[nc][ntiles]] of the STAGED side's tiles of PT
+// consecutive (grid-ordered, hence spatially compact) points.  For a fixed thread point p the reference's difference
+// df_k = fl(fl(x_k - z_k) + 1e-8) is monotone in the staged coordinate, so over the tile it lies in [a_k, b_k] with
+// a_k, b_k the same expression at the box corners; |df_k| >= dk = 0 if a_k <= 0 <= b_k else min(|a_k|, |b_k|), and
+// because rounding is monotone the sum below (same operations, same order as the pair loop) is a lower bound of
+// every pair's computed s.  reach_test(s, r2, ..) is false for every s > r2*(1+1e-12), so a tile whose lower bound
+// exceeds that for every open constraint of every thread is skipped without changing any result.
+// STAGED_IS_X: the thread holds z and the tile holds x (GoOSE target); otherwise the thread holds x (expander).
+// ---------------------------------------------------------------------------------------------
+template <int D, bool STAGED_IS_X>
+__device__ __forceinline__ double tile_lower_bound(const double (&p)[D], const double* __restrict__ bb, long long ntiles, long long tile) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double lo = bb[(size_t)k * ntiles + tile], hi = bb[(size_t)(D + k) * ntiles + tile];
+    double a, b;
+    if (STAGED_IS_X) {   // df = (x - z) + 1e-8, x in [lo, hi], z = p
+      a = __dadd_rn(__dsub_rn(lo, p[k]), SBO_PAIR_OFFSET); b = __dadd_rn(__dsub_rn(hi, p[k]), SBO_PAIR_OFFSET);
+    } else {             // x = p, z in [lo, hi]
+      a = __dadd_rn(__dsub_rn(p[k], hi), SBO_PAIR_OFFSET); b = __dadd_rn(__dsub_rn(p[k], lo), SBO_PAIR_OFFSET);
+    }
+    const double dk = (a <= 0.0 && b >= 0.0) ? 0.0 : fmin(fabs(a), fabs(b));
+    s = __dadd_rn(s, __dmul_rn(dk, dk));
+  }
+  return s;
+}
+
+// bounding boxes (and, with thr, the largest radius^2 per constraint) of tiles of PT consecutive points
+template <int D>
+__global__ void __launch_bounds__(PT)
+k_tile_bbox(long long n, long long ntiles, const double* __restrict__ coords, int nc, const double* __restrict__ thr,
+            double* __restrict__ bb) {
+  __shared__ double red[PT / 32];
+  const long long tile = blockIdx.x, i = tile * PT + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_reduce = [&](double v, bool want_max) -> double {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double w = __shfl_xor_sync(0xffffffffu, v, o);
+      v = want_max ? fmax(v, w) : fmin(v, w);
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double r = red[0];
+    for (int w = 1; w < PT / 32; ++w) r = want_max ? fmax(r, red[w]) : fmin(r, red[w]);
+    return r;
+  };
+  for (int k = 0; k < D; ++k) {
+    const double v = (i < n) ? coords[(size_t)k * n + i] : 0.0;
+    const double lo = block_reduce((i < n) ? v : INFINITY, false);
+    const double hi = block_reduce((i < n) ? v : -INFINITY, true);
+    if (threadIdx.x == 0) { bb[(size_t)k * ntiles + tile] = lo; bb[(size_t)(D + k) * ntiles + tile] = hi; }
+  }
+  for (int c = 0; c < nc; ++c) {
+    const double r = block_reduce((i < n && thr) ? thr[(size_t)c * n + i] : -1.0, true);
+    if (threadIdx.x == 0 && thr) bb[(size_t)(2 * D + c) * ntiles + tile] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // SafeOpt expander: one thread per candidate x, z tiles staged in shared memory.
 // hits[c][t] = 1 if some z is reachable from x_t under constraint c+1.
 // ---------------------------------------------------------------------------------------------
@@ -40,7 +100,8 @@ template <int D>
 __global__ void __launch_bounds__(PT)
 k_pairs_expander(PairConsts pc, long long nx, long long nz, const double* __restrict__ xc, const double* __restrict__ ucb,
                  const double* __restrict__ thr, const double* __restrict__ zc, unsigned char* __restrict__ hits,
-                 unsigned long long* __restrict__ pair_counter, long long z_per_split) {
+                 unsigned long long* __restrict__ pair_counter, long long z_per_split, const double* __restrict__ bb,
+                 long long ntiles) {
   __shared__ double zs[D][PT];
   const long long t = (long long)blockIdx.x * PT + threadIdx.x;
   const bool active = t < nx;
@@ -63,6 +124,15 @@ k_pairs_expander(PairConsts pc, long long nx, long long nz, const double* __rest
   unsigned long long tiles = 0;
   for (long long zb = z0; zb < z1; zb += PT) {
     if (__syncthreads_and((found | dead) == full)) break;
+    if (bb) {   // exact culling: skip the tile when no thread's x can reach its bounding box (see tile_lower_bound)
+      bool need = false;
+      if (active && (found | dead) != full) {
+        const double slb = tile_lower_bound<D, false>(x, bb, ntiles, zb / PT);
+        for (int c = 0; c < pc.nc; ++c)
+          if (!(((found | dead) >> c) & 1u) && slb <= r2[c] * (1.0 + 1e-12)) need = true;
+      }
+      if (!__syncthreads_or(need)) continue;
+    }
     const long long zi = zb + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < D; ++k) zs[k][threadIdx.x] = (zi < z1) ? zc[(size_t)k * nz + zi] : INFINITY;
@@ -97,7 +167,8 @@ template <int D>
 __global__ void __launch_bounds__(PT)
 k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restrict__ xc, const double* __restrict__ ucb,
                const double* __restrict__ thr, const double* __restrict__ zc, unsigned char* __restrict__ hits,
-               unsigned long long* __restrict__ pair_counter, long long x_per_split) {
+               unsigned long long* __restrict__ pair_counter, long long x_per_split, const double* __restrict__ bb,
+               long long ntiles) {
   __shared__ double xs[D][PT];
   __shared__ double us[SBO_MAX_G - 1][PT];
   __shared__ double rs[SBO_MAX_G - 1][PT];
@@ -115,6 +186,19 @@ k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restri
   unsigned long long tiles = 0;
   for (long long xb = x0; xb < x1; xb += PT) {
     if (__syncthreads_and(found == full)) break;
+    if (bb) {   // exact culling against the x tile's bounding box and its largest radius per constraint
+      bool need = false;
+      if (active && found != full) {
+        const long long tile = xb / PT;
+        const double slb = tile_lower_bound<D, true>(z, bb, ntiles, tile);
+        const double* r2max = bb + (size_t)2 * D * ntiles;
+        for (int c = 0; c < pc.nc; ++c) {
+          const double rm = r2max[(size_t)c * ntiles + tile];
+          if (!((found >> c) & 1u) && rm >= 0.0 && slb <= rm * (1.0 + 1e-12)) need = true;
+        }
+      }
+      if (!__syncthreads_or(need)) continue;
+    }
     const long long xi = xb + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < D; ++k) xs[k][threadIdx.x] = (xi < x1) ? xc[(size_t)k * nx + xi] : INFINITY;
@@ -148,9 +232,9 @@ k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restri
 }
 
 template <int D>
-static void launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long long nx, long long nz, const double* xc,
-                         const double* ucb, const double* thr, const double* zc, unsigned char* hits,
-                         unsigned long long* ctr) {
+static int launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long long nx, long long nz, const double* xc,
+                        const double* ucb, const double* thr, const double* zc, unsigned char* hits,
+                        unsigned long long* ctr) {
   const long long nthr = goose ? nz : nx, ntile = goose ? nx : nz;
   const long long bx = cdiv(nthr, PT);
   long long splits = 1;
@@ -158,10 +242,19 @@ static void launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long lo
   while (bx * splits < 4 * 148 && splits * 8 <= tiles && splits < 65535) splits *= 2;   // enough CTAs, >= 8 tiles each
   const long long per = cdiv(cdiv(ntile, splits), PT) * PT;
   dim3 grid((unsigned)bx, (unsigned)cdiv(ntile, per));
+  // bounding boxes of the staged side's tiles for the exact culling (option pair_cull, default on)
+  double* bb = nullptr;
+  if (ctx->opt_pair_cull) {
+    SBO_TRY(sbo_ensure(ctx, ctx->tile_bb, sizeof(double) * (size_t)(2 * D + pc.nc) * tiles));
+    bb = (double*)ctx->tile_bb.p;
+    k_tile_bbox<D><<<(unsigned)tiles, PT, 0, ctx->stream>>>(ntile, tiles, goose ? xc : zc, pc.nc, goose ? thr : nullptr, bb);
+    ctx->launches++;
+  }
   if (goose)
-    k_pairs_target<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per);
+    k_pairs_target<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles);
   else
-    k_pairs_expander<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per);
+    k_pairs_expander<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles);
+  return SBO_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -617,14 +710,14 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     unsigned char* hits = (unsigned char*)result_dev;
     ev_begin(ctx, 4);
     switch (d) {
-      case 1: launch_pairs<1>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      case 2: launch_pairs<2>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      case 3: launch_pairs<3>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      case 4: launch_pairs<4>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      case 5: launch_pairs<5>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      case 6: launch_pairs<6>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      case 7: launch_pairs<7>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
-      default: launch_pairs<8>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr); break;
+      case 1: SBO_TRY(launch_pairs<1>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 2: SBO_TRY(launch_pairs<2>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 3: SBO_TRY(launch_pairs<3>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 4: SBO_TRY(launch_pairs<4>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 5: SBO_TRY(launch_pairs<5>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 6: SBO_TRY(launch_pairs<6>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 7: SBO_TRY(launch_pairs<7>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      default: SBO_TRY(launch_pairs<8>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
     }
     SBO_LAUNCH_CHECK();
     ev_end(ctx);

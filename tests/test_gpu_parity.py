@@ -295,6 +295,39 @@ def test_expander_and_target_lipschitz(engine, oracle, request, name, n, beta, g
                 assert e_idx == eo and dist == pytest.approx(do, rel=1e-14)
 
 
+@pytest.mark.parametrize("name,n,beta,grid,mult", [("c1", 9, 3.0, [200, 160], 1.0), ("c1", 14, 3.0, [160, 200], 6.0),
+                                                   ("c3", 20, 2.0, [150, 170], 1.0), ("c3", 35, 2.0, [190, 130], 20.0)])
+def test_tile_culling_is_exact(engine, oracle, request, name, n, beta, grid, mult):
+    """The bounding-box culling of the Lipschitz pair kernels skips tiles only: every mask, optimum and index is
+    bit-identical to the un-culled all-pairs run, and fewer (never more) pairs are evaluated."""
+    capi = _capi()
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    engine.set_model(ds)
+    engine.set_grid(gold["lo"], gold["hi"], grid)
+    engine.posterior(with_grad=True, fetch=False)
+    engine.sets(beta, capi.UNSAFE_ALL)
+    G = ds["Y_norm"].shape[1]
+    L = np.full(G, engine.lipschitz()[G - 1] * mult)        # larger L = smaller radii = more culling
+    res = {}
+    for cull in (0, 1):
+        engine.set_option("pair_cull", cull)
+        ex = engine.expander(beta, L)
+        em = [engine.mask(capi.MASK_EXPANDER, c) for c in range(G - 1)]
+        tg = engine.goose_target(beta, L)
+        tm = [engine.mask(capi.MASK_TARGET, c) for c in range(G - 1)]
+        res[cull] = (ex, em, tg, tm)
+    engine.set_option("pair_cull", 1)
+    (ex0, em0, tg0, tm0), (ex1, em1, tg1, tm1) = res[0], res[1]
+    for c in range(G - 1):
+        assert np.array_equal(em0[c], em1[c]) and np.array_equal(tm0[c], tm1[c])
+    for k in ("best_idx", "best_value", "per_idx", "per_value", "n_hit", "pairs_algorithmic"):
+        assert ex0[k] == ex1[k] and tg0[k] == tg1[k], k
+    assert ex1["pairs_evaluated"] <= ex0["pairs_evaluated"] and tg1["pairs_evaluated"] <= tg0["pairs_evaluated"]
+    print(f"culling {name} n={n} x{mult}: expander {ex0['pairs_evaluated']} -> {ex1['pairs_evaluated']} pair-evals, "
+          f"target {tg0['pairs_evaluated']} -> {tg1['pairs_evaluated']}; hits {ex1['n_hit']}/{tg1['n_hit']}")
+
+
 @pytest.mark.parametrize("name,n,beta", [("c1", 9, 3.0), ("c3", 20, 2.0)])
 def test_whole_steps_match_oracle(engine, oracle, request, name, n, beta):
     gold = request.getfixturevalue(name)

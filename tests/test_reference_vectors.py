@@ -190,6 +190,24 @@ def test_oracle_grid_step_contains_reference_de_results(oracle, ref, name, n):
                              slack=CPU_SLACK)
 
 
+@pytest.mark.parametrize("name,n,seed", [("ref_c1_benoit", 4, 20260004), ("ref_c1_benoit", 14, 20260014),
+                                         ("ref_c3_wor", 20, 20260520)])
+def test_host_mirror_fit_reproduces_reference_fit(ref, name, n, seed):
+    """The drop-in GP class keeps the hyper-parameter fit on the host (GP_Safe.py:194-234): same SciPy DE call, so
+    under the RNG seed the generator used it lands on the reference's own optimum (NLL rounding differs slightly)."""
+    import sbo_b200  # noqa: F401
+    from sbo_b200.models.GP_Safe import GP
+    r = ref[name]
+    gp = GP([None] * r["Y"].shape[1])
+    np.random.seed(seed)
+    gp.GP_initialization(r["X"][:n], r["Y"][:n], 'RBF', multi_hyper=5, var_out=True)
+    assert np.max(np.abs(gp.hypopt - r[f"hypopt_{n}"])) <= 2e-3
+    for k in ("X_mean", "X_std", "Y_mean", "Y_std", "X_norm", "Y_norm"):
+        np.testing.assert_allclose(gp.inference_datasets[k], r[f"{k}_{n}"], rtol=1e-13, atol=1e-13)
+    with pytest.raises(ValueError):
+        gp.GP_initialization(r["X"][:n], r["Y"][:n], 'Matern', multi_hyper=5)        # GP_Safe.py:136-137
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU: the CUDA path (through the C ABI) vs the reference's own outputs
 # ------------------------------------------------------------------------------------------------
@@ -240,3 +258,37 @@ def test_cuda_plot_mask_and_step_vs_reference(engine, oracle, ref, name, n):
     gs = engine.goose_step(ds, beta)
     _check_goose_containment(oracle, r, n, dict(ds, invKopt=list(r[f"invKopt_{n}"])),
                              {"safe_min_lcb": gs["min_lcb0"], "target_lcb": gs["target_lcb"]})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n", [("ref_c1_benoit", 9), ("ref_c3_wor", 20)])
+def test_dropin_classes_vs_reference(oracle, ref, name, n):
+    """The reference's call sequence (test/test_SafeOpt.py:21-33,144-158; test/test_GoOSE.py:151-162) through the
+    drop-in classes, on the model state the reference's own fit produced."""
+    import sbo_b200  # noqa: F401
+    from sbo_b200.models import GoOSE, SafeOpt
+    r = ref[name]
+    G = r["Y"].shape[1]
+    plant = [lambda x, noise=0, j=j: 0.0 for j in range(G)]
+    beta = float(r["beta"])
+    ds = ref_ds(r, n)
+    bo = SafeOpt.BO(plant, r["bound"], beta)
+    bo.GP_initialization(r["X"][:n], r["Y"][:n], 'RBF', multi_hyper=5, var_out=True, hypopt=r[f"hypopt_{n}"])
+    for p, mo, vo, lo_, uo in zip(r[f"pts_{n}"][:6], r[f"mean_{n}"], r[f"var_{n}"], r[f"lcb_{n}"], r[f"ucb_{n}"]):
+        m, v = bo.GP_inference(p, bo.inference_datasets)
+        scale = np.maximum(np.abs(mo), ds["Y_std"])
+        assert np.all(np.abs(m - mo) <= 2e-8 * scale)
+        for i in range(G):
+            assert abs(bo.lcb(p, i) - lo_[i]) <= 1e-5 * scale[i] and abs(bo.ucb(p, i) - uo[i]) <= 1e-5 * scale[i]
+    x_min, std_min = bo.Minimizer()
+    x_exp, std_exp = bo.Expander()
+    _, min_ucb = bo.minimize_obj_ucb(None)
+    L = [0.0] + [bo.maximize_infnorm_mean_grad(i) for i in range(1, G)]
+    _check_safeopt_containment(oracle, r, n, ds, {"min_ucb0": min_ucb, "minimizer_std": std_min, "expander_std": std_exp, "L": L})
+    go = GoOSE.BO(plant, r["bound"], beta)
+    go.GP_initialization(r["X"][:n], r["Y"][:n], 'RBF', multi_hyper=5, var_out=True, hypopt=r[f"hypopt_{n}"])
+    _, lcb_min = go.minimize_obj_lcb()
+    z, lcb_t = go.Target()
+    x_e = go.explore_safeset(z)
+    _check_goose_containment(oracle, r, n, ds, {"safe_min_lcb": lcb_min, "target_lcb": lcb_t})
+    assert all(bo.lcb(x_e, i) >= 0 for i in range(1, G))                      # the exploration point is safe
