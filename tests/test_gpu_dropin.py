@@ -143,3 +143,43 @@ def test_wor_three_gps_fantasy_mode(oracle, c3):
             assert np.array_equal(bo.safe_mask('expander'), so["expander_masks"][0])
         assert std_exp == pytest.approx(so["expander_std"], rel=1e-6)
         assert np.array_equal(bo.safe_mask('safe'), so["S"])
+
+
+def test_safeopt_and_goose_runs_on_benoit_end_to_end(tmp_path):
+    """BASELINE.json configs[0]/[1] as the reference's drivers run them (test/test_SafeOpt.py:21-33,135-186;
+    test/test_GoOSE.py:142-190): 4 initial samples around (1.4,-0.8), hyper-fit on the host, every acquisition on the
+    GPU grid pipeline.  Checks what the reference's GIFs show: the runs stay safe and walk towards the constrained
+    optimum f = 0.145249 at (0.368,-0.393)."""
+    from sbo_b200 import drivers
+    from sbo_b200.models import GoOSE, SafeOpt
+    from sbo_b200.problems import Benoit_Problem as P
+    from sbo_b200.utils import utils_SafeOpt
+    plant = [P.Benoit_System_1, P.con1_system_tight]
+    bound = np.array([[-.6, 1.5], [-1., 1.]])
+    for algo in ("safeopt", "goose"):
+        bo = (SafeOpt.BO if algo == "safeopt" else GoOSE.BO)(plant, bound, 3.)
+        bo.key = np.random.default_rng(3)
+        bo.hyper_seed = 11
+        X, Y = bo.Data_sampling(4, np.array([1.4, -.8]), 0.3, 0.)
+        bo.GP_initialization(X, Y, 'RBF', multi_hyper=5, var_out=True)
+        f0 = Y[:, 0].min()
+        frames = []
+
+        def on_it(i, GP_m, x_new, y, info):
+            if i == 0:
+                X_0, X_1, mask, obj = utils_SafeOpt.create_data_for_plot(GP_m, plant, n_grid=100)
+                frames.append((mask.shape, int(mask.sum())))
+        data = (drivers.run_safeopt(bo, n_iteration=10, on_iteration=on_it) if algo == "safeopt"
+                else drivers.run_goose(bo, n_iteration=10, on_iteration=on_it))
+        con = np.array(data["con"])
+        obj = np.array(data["obj"])
+        assert frames and frames[0][0] == (100, 100) and frames[0][1] > 0
+        assert np.all(con >= -1e-9), (algo, con)                      # every query satisfied the true constraint
+        assert obj.min() < f0 and obj.min() < 0.6, (algo, obj)       # moved from f ~ 1.4 towards the optimum 0.145
+        assert bo.n_point == 4 + len(data["i"])
+    runs = drivers.run_multiple(lambda: SafeOpt.BO(plant, bound, 2.), [1.4, -.8], 0.3, 4, 2, 3, 0.005,
+                                path=tmp_path / "multi.npz", seeds=[5, 6])
+    back = drivers.load_runs(tmp_path / "multi.npz")
+    assert set(back) == {"0", "1"} and back["0"]["sampled_x"].shape == (4, 2)
+    assert back["1"]["observed_output"].shape[1] == 2 and 1 <= back["1"]["observed_x"].shape[0] <= 3
+    assert runs["0"]["observed_x"].shape == back["0"]["observed_x"].shape

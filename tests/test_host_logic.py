@@ -74,3 +74,93 @@ def test_workloads_deterministic():
     b = workloads.c4(pts_per_dim=8, n=32)
     assert np.array_equal(a[0]["X_norm"], b[0]["X_norm"]) and a[3] == [8, 8, 8, 8]
     assert a[0]["hypopt"].shape == (6, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# drivers.py: the reference's loops (test/test_SafeOpt.py:135-253, test/test_GoOSE.py:142-190) over a scripted BO
+# ------------------------------------------------------------------------------------------------
+class _ScriptedBO:
+    """Duck-typed BO whose acquisition answers are scripted: checks control flow only (no GPU)."""
+    nx_dim, n_fun = 2, 2
+
+    def __init__(self, script):
+        self.script, self.k, self.added = script, 0, []
+        self.plant_system = [lambda x, noise=0: float(x[0] ** 2 + x[1] ** 2), lambda x, noise=0: float(1.0 - x[0])]
+
+    def _cur(self):
+        return self.script[min(self.k, len(self.script) - 1)]
+
+    def Minimizer(self):
+        return np.array(self._cur()["min"][0]), self._cur()["min"][1]
+
+    def Expander(self):
+        return np.array(self._cur()["exp"][0]), self._cur()["exp"][1]
+
+    def ucb(self, x, j):
+        return self._cur().get("ucb", 1.0)
+
+    def minimize_obj_lcb(self):
+        return np.array(self._cur()["safe"][0]), self._cur()["safe"][1]
+
+    def Target(self):
+        return np.array(self._cur()["tgt"][0]), self._cur()["tgt"][1]
+
+    def explore_safeset(self, t):
+        return np.asarray(t) * 0.5
+
+    def calculate_plant_outputs(self, x, noise=0):
+        return np.array([f(x, noise) for f in self.plant_system])
+
+    def add_sample(self, x, y, hypopt=None):
+        self.added.append((np.asarray(x), np.asarray(y)))
+        self.k += 1
+
+
+def test_safeopt_driver_decision_rule_and_early_stop():
+    from sbo_b200 import drivers
+    bo = _ScriptedBO([{"min": ([0.1, 0.2], 0.5), "exp": ([0.3, 0.4], 0.2)},          # std_min > std_exp -> minimiser
+                      {"min": ([0.1, 0.2], 0.1), "exp": ([0.3, 0.4], 0.2)},          # else -> expander
+                      {"min": ([0.5, 0.5], 0.001), "exp": ([0.6, 0.6], 0.002)},      # both < 0.01 -> stop after adding
+                      {"min": ([9, 9], 1.0), "exp": ([9, 9], 1.0)}])
+    data = drivers.run_safeopt(bo, n_iteration=10)
+    assert data["i"] == [0, 1, 2] and len(bo.added) == 3                               # test_SafeOpt.py:175-179
+    assert [i["chose"] for i in data["info"]] == ["minimizer", "expander", "expander"]
+    assert data["x_0"][:2] == [0.1, 0.3] and data["obj"][0] == pytest.approx(0.05)
+    # multi-run guard (test_SafeOpt.py:228-240): an expander with every constraint ucb < 0 is not taken
+    bo = _ScriptedBO([{"min": ([0.1, 0.2], 0.1), "exp": ([0.3, 0.4], 0.2), "ucb": -1.0}])
+    x, info = drivers.safeopt_iteration(bo, require_lipschitz_ucb=True)
+    assert info["chose"] == "minimizer" and np.allclose(x, [0.1, 0.2])
+    # empty expander set: (nan, 0.0) never beats the minimiser
+    bo = _ScriptedBO([{"min": ([0.1, 0.2], 0.05), "exp": ([np.nan, np.nan], 0.0)}])
+    assert drivers.safeopt_iteration(bo)[1]["chose"] == "minimizer"
+
+
+def test_goose_driver_decision_rule():
+    from sbo_b200 import drivers
+    bo = _ScriptedBO([{"safe": ([0.2, 0.2], 0.10), "tgt": ([0.8, 0.8], 0.30)},        # min_safe_lcb <= target_lcb
+                      {"safe": ([0.2, 0.2], 0.50), "tgt": ([0.8, 0.4], 0.30)},        # else explore towards the target
+                      {"safe": ([0.2, 0.2], 0.50), "tgt": ([np.nan, np.nan], np.inf)}])   # empty target set
+    data = drivers.run_goose(bo, n_iteration=3, f_opt=None)
+    assert [i["chose"] for i in data["info"]] == ["safe_minimum", "explore", "safe_minimum"]
+    assert np.isnan(data["info"][0]["x_target"]).all()                                # test_GoOSE.py:160
+    assert (data["x_0"][1], data["x_1"][1]) == (0.4, 0.2)
+    stop = drivers.run_goose(_ScriptedBO([{"safe": ([0.3, 0.2], 0.1), "tgt": ([1, 1], 9.)}]), n_iteration=5,
+                             f_opt=0.13, tol=0.005)
+    assert stop["i"] == [0]                                                           # test_GoOSE.py:182
+
+
+def test_result_file_layout_matches_reference_consumers(tmp_path):
+    from sbo_b200 import drivers
+    data = {"0": {"sampled_x": np.zeros((4, 2)), "sampled_output": np.ones((4, 2)),
+                  "observed_x": np.zeros((3, 2)), "observed_output": np.arange(6.).reshape(3, 2)},
+            "1": {"sampled_x": np.zeros((4, 2)), "sampled_output": np.ones((4, 2)),
+                  "observed_x": np.zeros((2, 2)), "observed_output": np.arange(4.).reshape(2, 2)}}
+    p = tmp_path / "runs.npz"
+    drivers.save_runs(p, data)
+    raw = np.load(p, allow_pickle=True)
+    # the access pattern of the reference's utils/utils_solve_Benoit.py:16-31
+    n_start = len(raw.items())
+    shapes = [np.array(raw[f"{i}"].item()["observed_output"]).shape for i in range(n_start)]
+    assert shapes == [(3, 2), (2, 2)]
+    back = drivers.load_runs(p)
+    np.testing.assert_array_equal(back["1"]["observed_output"], data["1"]["observed_output"])
