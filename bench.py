@@ -233,9 +233,9 @@ def reference_configs(eng, torch, reps=5):
 # dram__bytes_read.sum + dram__bytes_write.sum of k_fantasy_tc per launch from the committed ncu capture
 # (profiles/): filled in when a capture of the same configuration exists, else null
 TRAFFIC_NCU = {
-    # profiles/r01_ncu_fantasy_tc2_summary.txt: k_fantasy_tc2<1,4> on C4/TF32, one launch = the whole pair stage:
-    # 123.59 GB read + 0.03 GB written (z tiles are re-read once per x raster group; 4 % of HBM bandwidth)
-    ("c4", "tf32"): 123.59e9 + 0.0285e9,
+    # profiles/r01_ncu_final_summary.txt: tc::k_fantasy_tc2<1,4> on C4/TF32, one launch = the whole pair stage:
+    # 120.23 GB read + 0.29 GB written (z tiles are re-read once per x raster group; 3.4 % of HBM bandwidth)
+    ("c4", "tf32"): 120.23e9 + 0.289e9,
 }
 
 
@@ -387,7 +387,7 @@ def run_ours(args):
             peak, src = mp["bf16_tflops_sustained"] / 2.0, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate), of measured"
         else:
             peak, src = peaks.get("tf32_tflops"), "cuBLAS TF32 GEMM measured in this run (MEASURED_PEAKS.json absent)"
-        roof = {"kernel": "k_fantasy_tc (fantasy expander GEMM, %s)" % args.precision, "bound": "tensor",
+        roof = {"kernel": "tc::k_fantasy_tc2 (fantasy expander GEMM, 2-CTA tcgen05, %s)" % args.precision, "bound": "tensor",
                 "achieved": flops / t_k / 1e12 if t_k > 0 else None,
                 "peak": peak, "unit": "TFLOP/s", "traffic": TRAFFIC_NCU.get((args.workload, args.precision)),
                 "peak_source": src, "cublas_tf32_tflops_this_run": peaks.get("tf32_tflops"),
