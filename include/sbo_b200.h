@@ -187,6 +187,14 @@ int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
  * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce */
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
+/* ---- hyper-parameter fit:  GP.negative_loglikelihood  (GP_Safe.py:169-192), batched ------
+ * NLL_p = y^T K_p^-1 y + log det K_p with K_p = sf2 exp(-1/2 dist) + (sn2 + 1e-8) I for P hyper-parameter vectors at
+ * once (a whole differential-evolution population of GP_Safe.py:224 instead of one individual per call).
+ * X_norm[n*d] row-major, y[n] (one output column of Y_norm), hyp[P*(d+2)] row p = (1/2 log ell_0..d-1,
+ * 1/2 log sf2, 1/2 log sn2) as GP_Safe.py:180-182, nll[P] out; a K_p that is not positive definite gives +inf.
+ * Does not touch the model installed by sbo_set_model. */
+int sbo_nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll);
+
 /* give device workspaces back to the driver (large grids: the V rows of the fantasy expander are n x count per
  * constraint -- 51 GB per rank at C5).  what = 1: the per-point V rows kept by sbo_posterior(keep_v) (call after
  * sbo_pairs_export_dev; a later fantasy prepare needs a new sbo_posterior); 2: the gathered pair operands

@@ -84,6 +84,7 @@ SIGNATURES = {
     "sbo_phase_ms": (C.c_int, [_P, C.c_int, _D]),
     "sbo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "sbo_release": (C.c_int, [_P, C.c_int]),
+    "sbo_nll_batch": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, C.c_int, _D, _D]),
 }
 
 _lib = None

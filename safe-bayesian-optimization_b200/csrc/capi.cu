@@ -89,7 +89,7 @@ int sbo_destroy(sbo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->Xn, &ctx->Yn, &ctx->alpha, &ctx->W, &ctx->Kmat, &ctx->info, &ctx->pts, &ctx->mean, &ctx->var,
-                    &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->tile_bb, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
+                    &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->tile_bb, &ctx->nll_K, &ctx->nll_in, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
                     &ctx->m_tgt, &ctx->partials, &ctx->result, &ctx->scan_a, &ctx->scan_b, &ctx->xs_idx, &ctx->zs_idx,
                     &ctx->xs_pay, &ctx->zs_pay, &ctx->hits, &ctx->counts, &ctx->pairctr, &ctx->imp_rows, &ctx->vx, &ctx->vz,
                     &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v, &ctx->m_prune})
@@ -376,6 +376,11 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms) {
   SBO_REQUIRE(phase >= 0 && phase < 8 && ms, "bad phase");
   *ms = ctx->phase_ms[phase];
   return SBO_OK;
+}
+
+int sbo_nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll) {
+  ENTER();
+  return nll_batch(ctx, n, d, X_norm, y, P, hyp, nll);
 }
 
 int sbo_release(sbo_ctx* ctx, int what) {

@@ -146,6 +146,7 @@ struct sbo_ctx {
   DevBuf vx, vz, aux_x, aux_z;
   DevBuf pp_x, pp_m, pp_v, pp_k, pp_g;   // scratch of the arbitrary-point posterior calls
   DevBuf tc_row, tc_col, tc_err;          // FP32 row/column records of the tcgen05 fantasy kernel
+  DevBuf nll_K, nll_in;                   // batched NLL (hyper-parameter fit): P x npad x npad factors, inputs/outputs
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
   PairStage ps;
@@ -206,6 +207,7 @@ static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b;
 int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const double* Y_norm,
                  const double* X_mean, const double* X_std, const double* Y_mean, const double* Y_std,
                  const double* hyp);
+int nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll);
 int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v);
 int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, double* var);
 int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad);

@@ -247,3 +247,124 @@ int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const 
   ctx->have_post = ctx->have_sets = ctx->have_sets2 = false;
   return SBO_OK;
 }
+
+
+// =============================================================================================
+// Batched negative log-likelihood for the hyper-parameter fit.
+//   GP.negative_loglikelihood (models/GP_Safe.py:169-192):  K = sf2*exp(-1/2 dist) + (sn2 + 1e-8) I,
+//   NLL = y^T K^-1 y + log det K = |L^-1 y|^2 + 2 sum log L_ii   with K = L L^T.
+// The reference evaluates it once per DE individual on the host (GP_Safe.py:224); here a whole DE population
+// (P hyper-parameter vectors) is factorised in one batch with the blocked-Cholesky kernels above (batch index in the
+// place of the GP index).
+// =============================================================================================
+// hyp[p][0..d) = 1/2 log ell_k, hyp[p][d] = 1/2 log sf2, hyp[p][d+1] = 1/2 log sn2      (GP_Safe.py:180-182)
+__global__ void k_build_K_pop(int n, int npad, int d, const double* __restrict__ Xn, const double* __restrict__ hyp,
+                              double* __restrict__ K) {
+  const int p = blockIdx.z;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npad || c >= npad) return;
+  const double* h = hyp + (size_t)p * (d + 2);
+  double v;
+  if (r < n && c < n) {
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double df = Xn[r * d + k] - Xn[c * d + k];
+      s += df * df / exp(2.0 * h[k]);
+    }
+    v = exp(2.0 * h[d]) * exp(-0.5 * s);
+    if (r == c) v += exp(2.0 * h[d + 1]) + 1e-8;                       // GP_Safe.py:184
+  } else {
+    v = (r == c) ? 1.0 : 0.0;
+  }
+  K[((size_t)p * npad + r) * npad + c] = v;
+}
+
+// one CTA per individual: t = L^-1 y by blocked forward substitution, NLL = |t|^2 + 2 sum log L_ii
+__global__ void __launch_bounds__(256) k_nll_finish(int n, int npad, const double* __restrict__ Lall, const double* __restrict__ y,
+                                                    const int* __restrict__ info, double* __restrict__ nll) {
+  extern __shared__ double sh[];        // t[npad] | tmp[NB]
+  double* t = sh;
+  double* tmp = sh + npad;
+  const int p = blockIdx.x;
+  const double* L = Lall + (size_t)p * npad * npad;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = 0; i < npad / NB; ++i) {
+    const int o = i * NB;
+    for (int rr = warp; rr < NB; rr += 8) {           // row o+rr: y_r - sum_{c<o} L[r][c] t[c]
+      const int r = o + rr;
+      double s = 0.0;
+      for (int c = lane; c < o; c += 32) s += L[(size_t)r * npad + c] * t[c];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+      if (lane == 0) tmp[rr] = ((r < n) ? y[r] : 0.0) - s;
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // 32x32 diagonal block, lane = row
+      double v = tmp[lane];
+      for (int j = 0; j < NB; ++j) {
+        const double tj = __shfl_sync(0xffffffffu, v, j) / L[(size_t)(o + j) * npad + o + j];
+        if (lane == j) v = tj;
+        else if (lane > j) v -= L[(size_t)(o + lane) * npad + o + j] * tj;
+      }
+      t[o + lane] = v;
+    }
+    __syncthreads();
+  }
+  double q = 0.0, ld = 0.0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) { q += t[r] * t[r]; ld += log(L[(size_t)r * npad + r]); }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) { q += __shfl_xor_sync(0xffffffffu, q, m); ld += __shfl_xor_sync(0xffffffffu, ld, m); }
+  __syncthreads();
+  if (lane == 0) { tmp[warp] = q; tmp[8 + warp] = ld; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double Q = 0.0, LD = 0.0;
+    for (int w = 0; w < 8; ++w) { Q += tmp[w]; LD += tmp[8 + w]; }
+    nll[p] = (info[p] != 0) ? INFINITY : Q + 2.0 * LD;
+  }
+}
+
+int nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll) {
+  SBO_REQUIRE(n >= 1 && n <= 8192, "n out of range");
+  SBO_REQUIRE(d >= 1 && d <= SBO_MAX_D, "d out of range (1..8)");
+  SBO_REQUIRE(P >= 1 && P <= 65535, "population size out of range (1..65535)");
+  SBO_REQUIRE(X_norm && y && hyp && nll, "null pointer");
+  const int np = (int)(cdiv(n, NB) * NB);
+  const size_t kbytes = sizeof(double) * (size_t)P * np * np;
+  SBO_TRY(sbo_ensure(ctx, ctx->nll_K, kbytes));
+  SBO_TRY(sbo_ensure(ctx, ctx->nll_in, sizeof(double) * ((size_t)n * d + n + (size_t)P * (d + 2) + P) + sizeof(int) * (size_t)P));
+  double* Xd = (double*)ctx->nll_in.p;
+  double* yd = Xd + (size_t)n * d;
+  double* hd = yd + n;
+  double* od = hd + (size_t)P * (d + 2);
+  int* info = (int*)(od + P);
+  SBO_CUDA(cudaMemcpyAsync(Xd, X_norm, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, ctx->stream));
+  SBO_CUDA(cudaMemcpyAsync(yd, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  SBO_CUDA(cudaMemcpyAsync(hd, hyp, sizeof(double) * (size_t)P * (d + 2), cudaMemcpyHostToDevice, ctx->stream));
+  SBO_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)P, ctx->stream));
+  double* K = (double*)ctx->nll_K.p;
+  {
+    dim3 b(16, 16), g((unsigned)cdiv(np, 16), (unsigned)cdiv(np, 16), (unsigned)P);
+    k_build_K_pop<<<g, b, 0, ctx->stream>>>(n, np, d, Xd, hd, K);
+    SBO_LAUNCH_CHECK();
+  }
+  const int nblk = np / NB;
+  for (int kb = 0; kb < nblk; ++kb) {
+    k_chol_diag<<<P, dim3(NB, NB), 0, ctx->stream>>>(K, np, kb, info);
+    SBO_LAUNCH_CHECK();
+    const int below = np - (kb + 1) * NB;
+    if (below > 0) {
+      k_chol_panel<<<dim3((unsigned)cdiv(below, 128), (unsigned)P), 128, 0, ctx->stream>>>(K, np, kb);
+      SBO_LAUNCH_CHECK();
+      const int nb = below / NB;
+      k_chol_update<<<dim3(nb, nb, P), dim3(NB, NB), 0, ctx->stream>>>(K, np, kb);
+      SBO_LAUNCH_CHECK();
+    }
+  }
+  k_nll_finish<<<P, 256, sizeof(double) * (np + NB), ctx->stream>>>(n, np, K, yd, info, od);
+  SBO_LAUNCH_CHECK();
+  SBO_CUDA(cudaMemcpyAsync(nll, od, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SBO_OK;
+}

@@ -101,6 +101,16 @@ class GridEngine:
                                          capi.dptr(ym), capi.dptr(ys), capi.dptr(hyp)))
         self.n, self.d, self.G = n, d, G
 
+    def nll_batch(self, X_norm, y, hyp_pop):
+        """GP.negative_loglikelihood (GP_Safe.py:169-192) for a population: hyp_pop (P, d+2) -> nll (P,)."""
+        Xn, yv, hp = _f64(X_norm), _f64(y).reshape(-1), _f64(hyp_pop)
+        n, d = Xn.shape
+        if hp.ndim != 2 or hp.shape[1] != d + 2 or yv.shape[0] != n:
+            raise ValueError("hyp_pop must be (P, d+2) and y (n,)")
+        out = np.empty(hp.shape[0])
+        self._ck(self._lib.sbo_nll_batch(self._h, n, d, capi.dptr(Xn), capi.dptr(yv), hp.shape[0], capi.dptr(hp), capi.dptr(out)))
+        return out
+
     def get_model(self):
         L = np.empty((self.G, self.n, self.n))
         W = np.empty((self.G, self.n, self.n))

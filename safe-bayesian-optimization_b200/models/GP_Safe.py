@@ -26,6 +26,7 @@ class GP:
                                    "X_norm": [], "Y_norm": [], "invKopt": [], "hypopt": []}
         self.GP_inference_jit = self.GP_inference     # reference: jit(self.GP_inference)
         self.hyper_seed = None                        # set to an int for a reproducible fit
+        self.fit_on_device = False                    # additive: evaluate whole DE populations on the GPU (sbo_nll_batch)
         self._device = device
         self._engine = None
         self._uploaded = None                         # id/version of the dataset resident on the GPU
@@ -113,8 +114,16 @@ class GP:
         invKopt = []
         for i in range(self.ny_dim):
             kw = {} if self.hyper_seed is None else {"seed": self.hyper_seed + i}
-            res = differential_evolution(self.negative_loglikelihood, args=(X_norm, Y_norm[:, i:i + 1]),
-                                         bounds=bounds, **kw)
+            if self.fit_on_device:
+                # same objective and bounds, but SciPy hands over the whole population (d+2, S) per generation and the
+                # GPU factorises the S covariance matrices in one batch; 'deferred' updating is what vectorised
+                # evaluation implies, so the search path (not the objective) differs from the reference's
+                yi = np.ascontiguousarray(Y_norm[:, i])
+                res = differential_evolution(lambda H: self.engine.nll_batch(X_norm, yi, np.atleast_2d(H.T)),
+                                             bounds=bounds, vectorized=True, updating='deferred', **kw)
+            else:
+                res = differential_evolution(self.negative_loglikelihood, args=(X_norm, Y_norm[:, i:i + 1]),
+                                             bounds=bounds, **kw)
             hypopt[:, i] = res.x
             ellopt = np.exp(2. * hypopt[:d, i])
             sf2opt = np.exp(2. * hypopt[d, i])

@@ -183,3 +183,41 @@ def test_safeopt_and_goose_runs_on_benoit_end_to_end(tmp_path):
     assert set(back) == {"0", "1"} and back["0"]["sampled_x"].shape == (4, 2)
     assert back["1"]["observed_output"].shape[1] == 2 and 1 <= back["1"]["observed_x"].shape[0] <= 3
     assert runs["0"]["observed_x"].shape == back["0"]["observed_x"].shape
+
+
+@pytest.mark.parametrize("n,d,P", [(4, 2, 60), (14, 2, 60), (35, 2, 33), (200, 4, 16), (600, 6, 5)])
+def test_batched_nll_matches_oracle(oracle, c3, n, d, P):
+    """sbo_nll_batch vs GP.negative_loglikelihood (GP_Safe.py:169-192) for a population inside the fit's bounds
+    (GP_Safe.py:205-206), including sizes that are not multiples of the 32-wide factorisation block."""
+    import sbo_b200
+    rng = np.random.default_rng(100 + n)
+    if d == 2 and n <= 35:
+        X, Y = c3["X"][:n], c3["Y"][:n]
+        Xn, Yn = oracle.normalize(X, Y)[4:]
+        y = Yn[:, 1]
+    else:
+        Xn = rng.normal(size=(n, d))
+        y = np.sin(Xn[:, 0]) + 0.1 * rng.normal(size=n)
+        y = (y - y.mean()) / y.std()
+    H = np.column_stack([rng.uniform(-1.5, 1.5, size=(P, d + 1)), rng.uniform(-5., -2., size=P)])
+    eng = sbo_b200.GridEngine(0)
+    got = eng.nll_batch(Xn, y, H)
+    want = np.array([oracle.negative_loglikelihood(h, Xn, y[:, None]) for h in H])
+    eng.close()
+    assert np.all(np.abs(got - want) <= 1e-9 * np.maximum(1.0, np.abs(want))), np.max(np.abs(got - want))
+
+
+def test_fit_on_device_reaches_the_host_optimum(c1):
+    """The DE fit with population NLLs on the GPU lands on (at least) the host fit's optimum."""
+    from sbo_b200.models.GP_Safe import GP
+    X, Y = c1["X"][:14], c1["Y"][:14]
+    host = GP([None, None]); host.hyper_seed = 5
+    host.GP_initialization(X, Y, 'RBF', multi_hyper=5)
+    dev = GP([None, None]); dev.hyper_seed = 5; dev.fit_on_device = True
+    dev.GP_initialization(X, Y, 'RBF', multi_hyper=5)
+    for i in range(2):
+        a = host.negative_loglikelihood(host.hypopt[:, i], host.X_norm, host.Y_norm[:, i:i + 1])
+        b = host.negative_loglikelihood(dev.hypopt[:, i], host.X_norm, host.Y_norm[:, i:i + 1])
+        assert b <= a + 1e-3 * max(1.0, abs(a)), (i, a, b)
+    m, v = dev.GP_inference(X[3], dev.inference_datasets)
+    assert np.all(np.abs(m - Y[3]) < 0.05)
