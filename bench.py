@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end repetitions (default max(2, steps); the first is dropped when > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
+    ap.add_argument("--no-lipschitz-steps", action="store_true", help="skip the reference-exact SafeOpt/GoOSE step times (extra key)")
     ap.add_argument("--no-reference-configs", action="store_true", help="skip the C1-C3 step times (extra key)")
     ap.add_argument("--prune", type=int, default=0, help="1: also time the step with the exact z-side pruning (extra key)")
     return ap.parse_args()
@@ -360,6 +361,32 @@ def run_ours(args):
         pruned = {"ms_per_step": float(np.mean(tp)) * 1e3, "pairs_evaluated": int(rp["expander"]["pairs_evaluated"]),
                   "x_new_idx": int(rp["x_new_idx"]), "n_hit": int(rp["expander"]["n_hit"]),
                   "note": "optional exact pruning (only optimistically-safe z are paired); same sets, not the headline"}
+    # ---- the reference-exact (Lipschitz) acquisition steps on the same workload: SafeOpt and GoOSE step time ----
+    lip = None
+    if not args.no_lipschitz_steps:
+        from sbo_b200 import sharded as _sh
+
+        def lip_step(goose):
+            with torch.cuda.stream(stream):
+                if world == 1:
+                    return eng.goose_step(ds, beta) if goose else eng.safeopt_step(ds, beta, mode="lipschitz", precision="fp64")
+                return _sh.goose_step(eng, ds, beta) if goose else _sh.safeopt_step(eng, ds, beta, mode="lipschitz", precision="fp64")
+        lip = {}
+        for goose in (False, True):
+            lip_step(goose)
+            tl = []
+            for _ in range(3):
+                flush.zero_(); barrier()
+                t0 = time.perf_counter(); rl = lip_step(goose); torch.cuda.synchronize(); tl.append(time.perf_counter() - t0)
+            t = torch.tensor([float(np.mean(tl))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pr = rl["target"] if goose else rl["expander"]
+            lip["goose" if goose else "safeopt"] = {"ms_per_step": float(t[0]) * 1e3, "pairs": int(pr["pairs_algorithmic"]),
+                                                    "pairs_evaluated": int(pr["pairs_evaluated"]), "n_hit": int(pr["n_hit"]),
+                                                    "x_new_idx": int(rl["x_new_idx"])}
+        lip["note"] = ("end-to-end wall time (host buffers) of one acquisition step with the reference's Lipschitz pair test "
+                       "(SafeOpt.py:85-124, GoOSE.py:80-119), exact tile culling on; max over ranks")
     pairs = int(ex["pairs_algorithmic"])            # sharded.safeopt_step already returns the global count
     if rank != 0:
         if world > 1:
@@ -415,6 +442,8 @@ def run_ours(args):
             "roofline": roof, "peaks": {**peaks, "hbm_gbs": mp.get("hbm_gbs"), "bf16_tflops": mp.get("bf16_tflops")}}
     if pruned is not None:
         line["pruned"] = pruned
+    if lip is not None:
+        line["lipschitz_mode"] = lip
     if world == 1 and not args.no_reference_configs:
         line["reference_configs"] = reference_configs(eng, torch)
     if not args.no_cpu_baseline and world == 1:

@@ -5,7 +5,7 @@ set +e
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 KREGEX="$1"; TAG="$2"; shift 2
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-peaks $*"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-peaks --no-reference-configs --no-lipschitz-steps $*"
 $CMD > gpurun_out/plain_${TAG}.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain_${TAG}.log; exit 1; }
 tail -c 600 gpurun_out/plain_${TAG}.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1

@@ -6,7 +6,7 @@
 set +e
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-B="--steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline --no-peaks --no-reference-configs"
+B="--steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline --no-peaks --no-reference-configs --no-lipschitz-steps"
 python bench.py $B > gpurun_out/plain_final_fantasy.log 2>&1 || { echo "plain fantasy run failed"; tail -20 gpurun_out/plain_final_fantasy.log; exit 1; }
 python bench.py --mode lipschitz --precision fp64 $B > gpurun_out/plain_final_lipschitz.log 2>&1 || { echo "plain lipschitz run failed"; exit 1; }
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_final_fantasy.csv python bench.py $B > gpurun_out/ncu_launches_final.log 2>&1

@@ -94,16 +94,16 @@ class OracleEngine:
             r[:, 2 * d + nc + c] = self.beta * np.sqrt(vn) / den
             r[:, 2 * d + 2 * nc + c] = 1.0 / den
         rows[: self.xs.size] = torch.from_numpy(r)
-        if vrows is not None:
+        if vrows is not None and self.xs.size:
             v = np.stack([self.V[c + 1][self.xs] for c in range(nc)], axis=1)          # (nx, nc, n)
             vrows[: self.xs.size] = torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(self.xs.size, -1))
 
     def pairs_import(self, n_total, rows, vrows):
-        self.rows = rows.numpy().copy()
+        self.rows = rows.numpy()[:n_total].copy()       # the buffers hold one placeholder row when n_total == 0
         self.n_total = n_total
         if vrows is not None:
             nc, n = self.G - 1, self.ds["X_norm"].shape[0]
-            self.Vx = vrows.numpy().copy().view(np.float64).reshape(n_total, nc, n)
+            self.Vx = vrows.numpy()[:n_total].copy().view(np.float64).reshape(n_total, nc, n)
 
     def pairs_run(self, goose, result):
         O, ds, d, nc = self.O, self.ds, self.d, self.G - 1
@@ -197,9 +197,14 @@ def _free_port():
     {"gold": "c1_benoit", "n": 9, "beta": 3.0, "grid": [36, 30], "mode": "lipschitz"},
     {"gold": "c3_wor", "n": 20, "beta": 2.0, "grid": [31, 37], "mode": "lipschitz"},
     {"gold": "c3_wor", "n": 20, "beta": 2.0, "grid": [22, 19], "mode": "fantasy"},
+    # three ranks, ragged last block and a partial last super-block of the rotated block-cyclic shards
+    {"gold": "c3_wor", "n": 35, "beta": 2.0, "grid": [29, 23], "mode": "lipschitz", "world": 3},
+    # empty safe set on every rank (huge beta): no candidates are exchanged, every optimum is "none"
+    {"gold": "c1_benoit", "n": 4, "beta": 500.0, "grid": [20, 17], "mode": "lipschitz"},
+    {"gold": "c1_benoit", "n": 4, "beta": 500.0, "grid": [20, 17], "mode": "fantasy"},
 ])
 def test_sharded_step_matches_single_process_oracle(oracle, case):
-    world = 2
+    world = case.get("world", 2)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -211,7 +216,8 @@ def test_sharded_step_matches_single_process_oracle(oracle, case):
         p.join(timeout=60)
     for r in results.values():
         assert "error" not in r, r.get("error")
-    assert results[0] == results[1]                      # every rank returns the same global answer
+    for rk in range(1, world):
+        assert results[0] == results[rk]                 # every rank returns the same global answer
     from conftest import load_golden, golden_ds
     gold = load_golden(case["gold"])
     ds = golden_ds(oracle, gold, case["n"])
