@@ -34,48 +34,69 @@ def create_data_for_plot(GP_m, plant_system, bound=None, n_grid=400, index=1):
     return X_0, X_1, mask_safe, obj
 
 
+# The optimum and the active constraint of the Benoit problem drawn on every frame (reference utils_SafeOpt.py:28-31)
+BENOIT_OPTIMUM = (0.36845785, -0.39299271)
+
+
+def _benoit_constraint_curve(n=400):
+    """u_0 = 1 + u_1^2 + 2 u_1 for u_1 in [-1.5, 1.5]: the boundary of con1_system_tight."""
+    u1 = np.linspace(-1.5, 1.5, n)
+    return 1. + u1 * (u1 + 2.), u1
+
+
+def draw_safe_region(ax, X, X_0, X_1, mask_safe, obj, bound, trajectory=None):
+    """Paint one frame on a matplotlib Axes: safe / unsafe shading from the grid mask, objective contours, the true
+    constraint boundary, the optimum, the initial samples and (optionally) the queried trajectory."""
+    shading = dict(levels=[0., 0.5, 1.], colors=['lightcoral', 'lightblue'], alpha=0.4)
+    ax.contourf(X_0, X_1, np.asarray(mask_safe, dtype=float), **shading)
+    if obj is not None:
+        iso = ax.contour(X_0, X_1, np.reshape(obj, np.shape(X_0)), colors='k', linestyles='dashed', linewidths=0.5)
+        ax.clabel(iso, inline=True)
+    ax.plot(*_benoit_constraint_curve(), color='k')
+    ax.plot(*BENOIT_OPTIMUM, marker='o', color='r', linestyle='none')
+    ax.plot(X[:, 0], X[:, 1], marker='o', color='b', linestyle='none')
+    if trajectory is not None:
+        q0, q1 = np.asarray(trajectory['x_0'], dtype=float), np.asarray(trajectory['x_1'], dtype=float)
+        ax.plot(q0, q1, marker='o', color='k', markersize=5, linewidth=0.5, label='_nolegend_')
+    lo_hi = np.asarray(bound, dtype=float)
+    ax.set_xlim(lo_hi[0])
+    ax.set_ylim(lo_hi[1])
+    return ax
+
+
 def plot_safe_region_Benoit(X, X_0, X_1, mask_safe, obj, bound, data=None):
-    plt = _plt()
-    plt.figure()
-    plt.contourf(X_0, X_1, mask_safe, levels=[0., 0.5, 1.], colors=['lightcoral', 'lightblue'], alpha=0.4)
-    CS1 = plt.contour(X_0, X_1, obj.reshape(X_0.shape), colors='k', linestyles='dashed', linewidths=0.5)
-    plt.clabel(CS1, inline=True)
-    x_0 = np.linspace(-1.5, 1.5, 400)
-    plt.plot(1. + x_0 ** 2 + 2. * x_0, x_0, 'k')            # tight constraint
-    plt.plot(0.36845785, -0.39299271, 'ro')                 # constrained optimum
-    plt.plot(X[:, 0], X[:, 1], 'bo')
-    if data is not None:
-        plt.plot(data['x_0'][:], data['x_1'][:], 'ko', linewidth=1., markersize=5)
-        plt.plot(data['x_0'][:], data['x_1'][:], 'k-', linewidth=0.5, label='_nolegend_')
-    plt.axis((bound[0, 0], bound[0, 1], bound[1, 0], bound[1, 1]))
+    """Reference signature (utils_SafeOpt.py:14-43): opens a new current figure and draws the frame on it."""
+    fig = _plt().figure()
+    draw_safe_region(fig.gca(), np.asarray(X), X_0, X_1, mask_safe, obj, bound, data)
 
 
 def create_frame(fun_drawing, filename):
+    """Reference signature (utils_SafeOpt.py:45-48): the drawing call has already run as the argument expression;
+    write the current figure to ``filename`` and release it."""
     plt = _plt()
-    plt.savefig(filename)
-    plt.close()
+    plt.gcf().savefig(filename)
+    plt.close('all')
 
 
 def create_GIF(frame_duration, filenames, GIFname, output_dir='output'):
-    import imageio.v2 as imageio
-    with imageio.get_writer(os.path.join(output_dir, GIFname), mode='I', duration=frame_duration, loop=0) as writer:
-        for filename in filenames:
-            writer.append_data(imageio.imread(filename))
-    for filename in filenames:
-        os.remove(filename)
+    """Reference signature (utils_SafeOpt.py:50-60): assemble the frames into output_dir/GIFname, then delete them."""
+    import imageio.v2 as iio
+    frames = [iio.imread(f) for f in filenames]
+    iio.mimsave(os.path.join(output_dir, GIFname), frames, duration=frame_duration, loop=0)
+    for f in filenames:
+        os.remove(f)
 
 
 def plant_outputs_drawing(iteration, output, constraint, figname, output_dir='output'):
-    plt = _plt()
-    plt.figure()
-    fig, axs = plt.subplots(2, 1, figsize=(5, 10))
-    axs[0].plot(iteration, output)
-    axs[0].set_xlabel('Iteration', fontsize=14)
-    axs[0].set_ylabel('Plant Output', fontsize=14)
-    axs[1].plot(iteration, constraint)
-    axs[1].plot(iteration, np.array([0.] * len(iteration)), 'r--', label='safety threshold')
-    axs[1].set_xlabel('Iteration', fontsize=14)
-    axs[1].set_ylabel('Plant Constraint', fontsize=14)
-    axs[1].legend()
-    plt.tight_layout()
-    plt.savefig(os.path.join(output_dir, figname))
+    """Reference signature (utils_SafeOpt.py:62-84): objective and constraint of the queried points per iteration,
+    with the safety threshold g = 0."""
+    fig, (top, bottom) = _plt().subplots(nrows=2, ncols=1, figsize=(5, 10))
+    it = np.asarray(iteration)
+    for ax, series, label in ((top, output, 'Plant Output'), (bottom, constraint, 'Plant Constraint')):
+        ax.plot(it, np.asarray(series, dtype=float))
+        ax.set_xlabel('Iteration', fontsize=14)
+        ax.set_ylabel(label, fontsize=14)
+    bottom.axhline(0., color='r', linestyle='--', label='safety threshold')
+    bottom.legend()
+    fig.tight_layout()
+    fig.savefig(os.path.join(output_dir, figname))

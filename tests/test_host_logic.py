@@ -65,7 +65,7 @@ def test_plants():
     assert abs(wo.get_objective(u) - 16.4139329) < 30.0
     assert wo.get_constraint1(u) == pytest.approx(2.18462911e-02, abs=5e-3)
     assert wo.get_constraint2(u) == pytest.approx(3.44493646e-02, abs=5e-3)
-    sol, _ = wo._solve(u, 0.0)
+    sol, _ = wo.steady_state(u, 0.0)
     assert np.max(np.abs(wo.odecallback(sol, u, 0.0))) < 1e-10
 
 
@@ -164,3 +164,20 @@ def test_result_file_layout_matches_reference_consumers(tmp_path):
     assert shapes == [(3, 2), (2, 2)]
     back = drivers.load_runs(p)
     np.testing.assert_array_equal(back["1"]["observed_output"], data["1"]["observed_output"])
+
+
+def test_plants_match_the_references_own_outputs():
+    """problems/*.py (NumPy restatements used as fixtures) vs outputs of the reference's own plants at noise = 0
+    (tests/golden/make_plant_vectors.py ran /root/reference/problems/*.py over the NumPy jax stand-in)."""
+    from conftest import load_golden
+    r = load_golden("ref_plants")
+    for u, f1, f2, c1, c1t in zip(r["benoit_u"], r["benoit_f1"], r["benoit_f2"], r["benoit_con1"], r["benoit_con1_tight"]):
+        assert Benoit_Problem.Benoit_System_1(u) == pytest.approx(f1, rel=1e-14, abs=1e-15)
+        assert Benoit_Problem.Benoit_System_2(u) == pytest.approx(f2, rel=1e-14, abs=1e-15)
+        assert Benoit_Problem.con1_system(u) == pytest.approx(c1, rel=1e-14, abs=1e-15)
+        assert Benoit_Problem.con1_system_tight(u) == pytest.approx(c1t, rel=1e-14, abs=1e-15)
+    wo = WilliamOttoReactor_Problem.WilliamOttoReactor()
+    for u, f, g1, g2 in zip(r["wor_u"], r["wor_obj"], r["wor_con1"], r["wor_con2"]):
+        assert wo.get_objective(u) == pytest.approx(f, rel=1e-10)
+        assert wo.get_constraint1(u) == pytest.approx(g1, abs=1e-12)
+        assert wo.get_constraint2(u) == pytest.approx(g2, abs=1e-12)
