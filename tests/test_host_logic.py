@@ -181,3 +181,45 @@ def test_plants_match_the_references_own_outputs():
         assert wo.get_objective(u) == pytest.approx(f, rel=1e-10)
         assert wo.get_constraint1(u) == pytest.approx(g1, abs=1e-12)
         assert wo.get_constraint2(u) == pytest.approx(g2, abs=1e-12)
+
+
+def test_plot_helpers_run_against_a_recording_matplotlib(tmp_path, monkeypatch):
+    """matplotlib / imageio are not installed in this image (they are imported lazily): run the helpers against
+    recording stand-ins to check the call sequence and the reference signatures (utils_SafeOpt.py:14-84)."""
+    import sys
+    import types
+    from unittest import mock
+    plt = mock.MagicMock(name="pyplot")
+    top, bottom, fig2 = mock.MagicMock(), mock.MagicMock(), mock.MagicMock()
+    plt.subplots.return_value = (fig2, (top, bottom))
+    mpl = types.ModuleType("matplotlib")
+    mpl.use = mock.MagicMock()
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    iio = mock.MagicMock(name="imageio.v2")
+    pkg = types.ModuleType("imageio")
+    pkg.v2 = iio
+    monkeypatch.setitem(sys.modules, "imageio", pkg)
+    monkeypatch.setitem(sys.modules, "imageio.v2", iio)
+    from sbo_b200.utils import utils_GoOSE, utils_SafeOpt
+    x0, x1 = np.meshgrid(np.linspace(-.6, 1.5, 5), np.linspace(-1, 1, 4))
+    mask = x0 > 0.3
+    X = np.array([[1.4, -0.8], [1.3, -0.7]])
+    bound = np.array([[-.6, 1.5], [-1., 1.]])
+    data = {"x_0": [1.2, 1.0], "x_1": [-0.7, -0.6], "x_target_0": 0.5, "x_target_1": -0.4}
+    utils_SafeOpt.create_frame(utils_SafeOpt.plot_safe_region_Benoit(X, x0, x1, mask, x0 ** 2 + x1 ** 2, bound, data),
+                               str(tmp_path / "f0.png"))
+    ax = plt.figure.return_value.gca.return_value
+    assert ax.contourf.called and ax.contour.called and ax.plot.call_count >= 4
+    plt.gcf.return_value.savefig.assert_called_with(str(tmp_path / "f0.png"))
+    n_before = ax.plot.call_count
+    utils_GoOSE.plot_safe_region_Benoit(X, x0, x1, mask, x0 ** 2 + x1 ** 2, bound, data)
+    assert ax.plot.call_count >= n_before + 6                      # the frame again + target marker + dashed line
+    utils_SafeOpt.plant_outputs_drawing([0, 1], [1.0, 0.5], [0.2, 0.1], "out.png", output_dir=str(tmp_path))
+    assert top.plot.called and bottom.axhline.called
+    fig2.savefig.assert_called_with(str(tmp_path / "out.png"))
+    f = tmp_path / "frame.png"
+    f.write_bytes(b"x")
+    utils_SafeOpt.create_GIF(700, [str(f)], "run.gif", output_dir=str(tmp_path))
+    assert iio.mimsave.called and not f.exists()
