@@ -2,16 +2,20 @@
 """bench.py -- SafeOpt/GoOSE grid step on N B200s: expander pair-evals/s (+ step time).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c4|c5|c4s] [--mode fantasy|lipschitz] [--precision tf32|fp64]
+                    [--workload c4|c5|c4s] [--mode fantasy|lipschitz] [--precision tf32|tf32x3|fp64]
 
 A "step" = model upload -> GP posterior over the grid for all G GPs -> safe/minimiser/unsafe sets ->
 Lipschitz constants (Lipschitz mode) -> expander pair kernel -> arg-reductions -> x_new.  It EXCLUDES the
 plant evaluation and the hyper-parameter fit, which stay on the host in the reference too.
 Workload at N=1: BASELINE.json configs[3] "synthetic SafeOpt expander step: 2^20-point d=4 grid, n=512
 observations, 3 constraint GPs" (C4); the grid is sharded over the ranks (strong scaling, fixed N).
-`value` = pair-evals of the whole job / device time of the step (CUDA events on the launch stream, max
-over ranks); `e2e` = the same through GridEngine.safeopt_step with HOST buffers (model H2D, result and
-safe-mask D2H inside the timed region, wall clock around a device sync).
+`value` = pair-evals of the whole job / device time of the step (CUDA events on the launch stream, every timed step
+preceded by a barrier, max over ranks); `e2e` = the same through GridEngine.safeopt_step / sharded.safeopt_step with
+HOST buffers (model H2D, result and safe-mask D2H inside the timed region, wall clock around a device sync).
+Extra keys: `roofline` (the fantasy GEMM against the measured TF32 peak, DRAM traffic from the committed ncu capture),
+`cpu_baseline` (N=1: the oracle on the host cores on a bounded sample), `lipschitz_mode` (step time of the
+reference-exact SafeOpt and GoOSE steps on the same workload, any N), `reference_configs` (N=1: C1-C3, the
+reference's own problems on its 400x400 grid), `phase_ms`, `clocks`, `gpu_launches`.
 --impl reference times the NumPy oracle (the port of the reference's arithmetic; JAX is not installed)
 on the host cores on a bounded sample of the same workload.
 """
