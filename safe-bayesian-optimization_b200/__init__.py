@@ -2,7 +2,8 @@
 
 Layout: ``csrc/`` (sm_100a kernels + the C ABI of include/sbo_b200.h), ``_capi`` (ctypes binding),
 ``engine`` (host driver) and the host-side mirror of the reference interface:
-``models.GP_Safe``, ``models.SafeOpt``, ``models.GoOSE``, ``utils.utils_SafeOpt``, ``utils.utils_GoOSE``,
+``models.GP_Safe``, ``models.SafeOpt``, ``models.GoOSE``, ``models.GP_TR``, ``utils.utils_SafeOpt``, ``utils.utils_GoOSE``,
+``drivers`` (the reference's BO loops),
 ``problems`` (NumPy restatements of the black-box plants used as fixtures).
 
 The directory name is not a Python identifier; import it as ``sbo_b200`` (repo-root shim) or put this

@@ -221,3 +221,38 @@ def test_fit_on_device_reaches_the_host_optimum(c1):
         assert b <= a + 1e-3 * max(1.0, abs(a)), (i, a, b)
     m, v = dev.GP_inference(X[3], dev.inference_datasets)
     assert np.all(np.abs(m - Y[3]) < 0.05)
+
+
+def test_trust_region_minimize_obj_lcb(oracle, c1):
+    """models/GP_TR.BO.minimize_obj_lcb(r, x_0) (reference GP_TR.py:43-51): argmin lcb_0 over the safe set within the
+    ball -- the grid pipeline with one extra (user) mask -- vs the oracle on the same grid."""
+    from sbo_b200.models import GP_TR
+    from sbo_b200.problems import Benoit_Problem as P
+    TRp = {'radius': 0.5, 'radius_max': 1, 'radius_red': 0.8, 'radius_inc': 1.1, 'rho_lb': 0.2, 'rho_ub': 0.8}
+    bound = np.array([[-.6, 1.5], [-1., 1.]])
+    n, beta, side = 9, 3.0, 120
+    bo = GP_TR.BO([P.Benoit_System_1, P.con1_system_tight], bound, beta, TRp, grid_points_per_dim=side)
+    bo.GP_initialization(c1["X"][:n], c1["Y"][:n], 'RBF', multi_hyper=5, var_out=True, hypopt=c1[f"hyp_{n}"])
+    ds = golden_ds(oracle, c1, n)
+    pts = oracle.make_grid(bound[:, 0], bound[:, 1], [side, side])
+    m, v = bo.grid_posterior()
+    lcb, _ = oracle.bounds(m, v, beta)
+    S = oracle.safe_mask(lcb)
+    for x_0, r in (([1.4, -0.8], 0.3), ([0.5, -0.3], 0.25), ([-0.5, 0.9], 0.2)):
+        dist = np.linalg.norm(pts - np.asarray(x_0), axis=1)
+        assert not np.any(np.abs(dist - r) < 1e-12)              # no grid point sits on the sphere: the ball is unambiguous
+        ball = dist <= r
+        io, vo = oracle.masked_argmin(lcb[:, 0], S & ball)
+        x, val = bo.minimize_obj_lcb(r, np.asarray(x_0))
+        if io < 0:
+            assert np.isnan(x).all() and val == np.inf
+        else:
+            np.testing.assert_allclose(x, pts[io], rtol=0, atol=1e-14)
+            assert val == pytest.approx(vo, rel=1e-14) and bo.TR_constraint(x, np.asarray(x_0), r) >= -1e-7
+    # one trust-region iteration as the reference's driver does (test/test_GP_TR.py:50-57)
+    x_old, r_old = np.array([1.4, -0.8]), 0.3
+    y_old = bo.calculate_plant_outputs(x_old)
+    x_min, _ = bo.minimize_obj_lcb(r_old, x_old)
+    centre, radius = bo.update_TR(x_old, x_min, r_old, y_old, bo.calculate_plant_outputs(x_min))
+    assert radius in (pytest.approx(r_old * 0.8), pytest.approx(r_old), pytest.approx(min(r_old * 1.1, 1)))
+    assert np.array_equal(centre, x_old) or np.array_equal(centre, x_min)

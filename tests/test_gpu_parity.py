@@ -578,3 +578,35 @@ def test_fantasy_tensor_core_synthetic(engine, oracle, variant, precision):
         print(f"fantasy {precision} v{variant} synthetic d={d} n={n}: {r}")
         if precision == "tf32x3":
             assert r["diff_vs_fp64"] <= max(2, r["newly_safe_fp64"] // 1000)
+
+
+def test_user_mask_argreductions(engine, oracle, c3):
+    """sbo_set_user_mask + sbo_argreduce over an arbitrary caller-supplied mask (all four reductions), lowest index on
+    ties, -1 for an empty mask."""
+    capi = _capi()
+    ds = golden_ds(oracle, c3, 20)
+    beta = 2.0
+    grid = [67, 45]                                           # 3015 points: not a multiple of 32
+    engine.set_model(ds)
+    engine.set_grid(c3["lo"], c3["hi"], grid)
+    m, v = engine.posterior()
+    engine.sets(beta, capi.UNSAFE_ALL)                        # installs beta for the lcb/ucb reductions
+    pts = oracle.make_grid(c3["lo"], c3["hi"], grid)
+    lcb, ucb = oracle.bounds(m, v, beta)
+    rng = np.random.default_rng(5)
+    for mask in (rng.random(pts.shape[0]) < 0.3, np.arange(pts.shape[0]) % 97 == 5, np.zeros(pts.shape[0], bool)):
+        engine.set_user_mask(mask)
+        assert np.array_equal(engine.mask(capi.MASK_USER), mask)
+        for kind, vals, want_max in ((capi.ARGMAX_VAR0, v[:, 0], True), (capi.ARGMIN_LCB0, lcb[:, 0], False),
+                                     (capi.ARGMIN_UCB0, ucb[:, 0], False)):
+            idx, val = engine.argreduce(kind, capi.MASK_USER)
+            io, vo = (oracle.masked_argmax if want_max else oracle.masked_argmin)(vals, mask)
+            assert idx == io
+            if io >= 0:
+                assert val == pytest.approx(vo, rel=1e-14)
+        t = np.array([5.5, 81.0])
+        idx, dist = engine.argreduce(capi.ARGMIN_DIST, capi.MASK_USER, 0, t)
+        io, do = oracle.explore_safeset(pts, mask, t)
+        assert idx == io
+        if io >= 0:
+            assert dist == pytest.approx(do, rel=1e-14)

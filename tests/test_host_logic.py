@@ -223,3 +223,28 @@ def test_plot_helpers_run_against_a_recording_matplotlib(tmp_path, monkeypatch):
     f.write_bytes(b"x")
     utils_SafeOpt.create_GIF(700, [str(f)], "run.gif", output_dir=str(tmp_path))
     assert iio.mimsave.called and not f.exists()
+
+
+def test_trust_region_update_rule():
+    """models/GP_TR.update_TR (reference GP_TR.py:56-91) is host control flow: check every branch with a scripted
+    posterior mean."""
+    from sbo_b200.models import GP_TR
+    P = {'radius': 0.5, 'radius_max': 1, 'radius_red': 0.8, 'radius_inc': 1.1, 'rho_lb': 0.2, 'rho_ub': 0.8}
+    bo = GP_TR.BO([None, None], np.array([[-.6, 1.5], [-1., 1.]]), 3., P)
+    means = {}
+    bo.GP_inference_jit = lambda x, ds: (np.array([means[tuple(x)], 0.0]), np.zeros(2))
+    x0, x1 = (1.4, -0.8), (1.2, -0.7)
+    means[x0], means[x1] = 2.0, 1.0                                       # predicted change -1
+    assert bo.update_TR(x0, x1, 0.5, [2.0, 0.3], [1.5, -0.1]) == (x0, 0.4)            # constraint violated -> shrink
+    assert bo.update_TR(x0, x1, 0.5, [2.0, 0.3], [2.1, 0.1]) == (x0, 0.4)             # objective went up -> shrink
+    assert bo.update_TR(x0, x1, 0.5, [2.0, 0.3], [1.9, 0.1]) == (x0, 0.4)             # rho = 0.1 < rho_lb
+    assert bo.update_TR(x0, x1, 0.5, [2.0, 0.3], [1.5, 0.1]) == (x1, 0.5)             # rho = 0.5 -> accept, keep r
+    assert bo.update_TR(x0, x1, 0.5, [2.0, 0.3], [1.1, 0.1]) == (x1, pytest.approx(0.55))   # rho = 0.9 -> grow
+    assert bo.update_TR(x0, x1, 0.95, [2.0, 0.3], [1.1, 0.1]) == (x1, 1)              # capped at radius_max
+    assert bo.TR_constraint(np.array([1.0, 0.0]), np.array([1.0, 0.3]), 0.5) == pytest.approx(0.2, abs=1e-7)
+    # ball mask geometry: x_0 fastest, numpy.linspace axes
+    bo.grid_points_per_dim = [5, 3]
+    bo._grid_set = True
+    bo.grid_shape = (5, 3)
+    m = bo._ball_mask([1.5, 1.0], 0.6).reshape(3, 5)
+    assert m[2, 4] and m[2, 3] and not m[2, 2] and not m[1, 4] and m.sum() == 2
