@@ -184,8 +184,14 @@ int sbo_pairs_finish_dev(sbo_ctx* ctx, int goose, int64_t offset, const void* re
 /* number of kernels this library launched on ctx since the last reset */
 int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
 /* device time of named phases of the last calls, milliseconds (CUDA events on the ctx stream).
- * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce */
+ * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce, 6 pair preparation */
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
+/* tuning / diagnosis options (defaults reproduce the documented behaviour; none changes a result):
+ *   "posterior_variant"  1 (default) FP64 tensor cores (DMMA) | 0 FP64 SIMT register tiles
+ *   "fantasy_variant"    -1 (default) auto | bit 0: 256-column z tiles, bit 1: 8 epilogue warps, bit 2: 2-CTA pairs
+ *   "fantasy_gx"         x tile pairs per raster group of the 2-CTA GEMM (0 = default: a quarter of the clusters)
+ *   "fantasy_prune"      1: pair only the optimistically-safe part of Z (exact; default 0)
+ *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
 /* ---- hyper-parameter fit:  GP.negative_loglikelihood  (GP_Safe.py:169-192), batched ------
  * NLL_p = y^T K_p^-1 y + log det K_p with K_p = sf2 exp(-1/2 dist) + (sn2 + 1e-8) I for P hyper-parameter vectors at
