@@ -292,3 +292,42 @@ def test_dropin_classes_vs_reference(oracle, ref, name, n):
     x_e = go.explore_safeset(z)
     _check_goose_containment(oracle, r, n, ds, {"safe_min_lcb": lcb_min, "target_lcb": lcb_t})
     assert all(bo.lcb(x_e, i) >= 0 for i in range(1, G))                      # the exploration point is safe
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU: the pair constraints of Expander()/Target() (SafeOpt.py:73-77,85-88,99-111; GoOSE.py:93-101)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n", [("ref_c1_benoit", 9), ("ref_c1_benoit", 14), ("ref_c3_wor", 20), ("ref_c3_wor", 35)])
+def test_oracle_pair_constraints_match_reference(oracle, ref, name, n):
+    """tests/golden/ref_pairs.npz: values of the reference's own constraint lambdas at random (x, z) pairs.
+    The oracle's safe / unsafe masks and its Lipschitz reach predicate must take the same decisions (pairs whose
+    reference value is within 1e-9 of the threshold are exempt)."""
+    rp = load_golden("ref_pairs")
+    r = ref[name]
+    ds = ref_ds(r, n)
+    beta = float(r["beta"])
+    key = f"{name}_{n}"
+    x, z, L = rp[key + "_x"], rp[key + "_z"], rp[key + "_L"]
+    G = ds["Y_norm"].shape[1]
+    mx, vx = oracle.posterior_inv(x, ds)
+    lcb_x, ucb_x = oracle.bounds(mx, vx, beta)
+    scale = np.maximum(np.max(np.abs(mx), axis=0), ds["Y_std"])
+    assert np.all(np.abs(lcb_x - rp[key + "_lcb_x"]) <= 1e-6 * scale)
+    clear = np.all(np.abs(rp[key + "_lcb_x"][:, 1:]) > 1e-9 * scale[1:], axis=1)
+    assert np.array_equal(oracle.safe_mask(lcb_x)[clear], np.all(rp[key + "_lcb_x"][:, 1:] >= 0, axis=1)[clear])
+    mz, vz = oracle.posterior_inv(z, ds)
+    lcb_z, _ = oracle.bounds(mz, vz, beta)
+    ref_max = rp[key + "_lcbmax_z"]                                   # lcb_constraint_min returns the MAX (sic)
+    assert np.all(np.abs(np.max(lcb_z[:, 1:], axis=1) - ref_max) <= 1e-6 * np.max(scale[1:]))
+    clear = np.abs(ref_max) > 1e-9 * np.max(scale[1:])
+    assert np.array_equal(oracle.unsafe_mask(lcb_z, "all")[clear], (ref_max <= 0)[clear])
+    # Lipschitz reach predicate, pair (x_j, z_j), constraint index idx, L of the LAST constraint (SafeOpt.py:110)
+    for c in range(G - 1):
+        reach = np.concatenate([blk for _, blk in oracle.pair_reach(x, ucb_x[:, c + 1], z, L[G - 1])], axis=0)
+        got = np.diag(reach)
+        want = rp[key + "_lip"][:, c]
+        clear = np.abs(want) > 1e-9 * scale[c + 1]
+        assert np.array_equal(got[clear], (want >= 0)[clear]), (c, int((got[clear] != (want >= 0)[clear]).sum()))
+        # and the value itself: ucb_idx(x) - L * ||x - z + 1e-8||
+        val = ucb_x[:, c + 1] - L[G - 1] * np.sqrt(np.sum((x - z + oracle.PAIR_OFFSET) ** 2, axis=1))
+        assert np.all(np.abs(val - want) <= 1e-6 * scale[c + 1])
