@@ -105,3 +105,52 @@ def test_empty_sets(oracle, c1):
     assert st["S"].sum() == 0 and st["minimizer_idx"] == -1 and st["expander_idx"] == -1 and st["x_new_idx"] == -1
     gs = oracle.goose_step(pts, ds, 3.0)
     assert gs["safe_min_idx"] == -1 and gs["target_idx"] == -1
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties of the set definitions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,beta", [("c1", 9, 3.0), ("c3", 20, 2.0), ("c3", 35, 2.0)])
+def test_set_algebra_and_monotonicity(oracle, request, name, n, beta):
+    gold = request.getfixturevalue(name)
+    ds = golden_ds(oracle, gold, n)
+    pts = oracle.make_grid(gold["lo"], gold["hi"], [48, 40])
+    m, v = oracle.posterior_inv(pts, ds)
+    G = m.shape[1]
+    lcb, ucb = oracle.bounds(m, v, beta)
+    S, Z_all, Z_any = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, "all"), oracle.unsafe_mask(lcb, "any")
+    assert not np.any(S & Z_any) and np.array_equal(Z_any, ~S)            # 'any' is the complement of S
+    assert np.all(Z_all <= (Z_any | np.all(lcb[:, 1:] == 0.0, axis=1)))    # 'all' is contained in it (up to lcb == 0)
+    _, _, M, min_ucb = oracle.minimizer(v, lcb, ucb, S)
+    assert np.all(M <= S) and (not S.any() or np.all(lcb[M, 0] <= min_ucb))
+    # a larger beta can only shrink the safe set (lcb decreases pointwise)
+    lcb2, ucb2 = oracle.bounds(m, v, beta * 1.5)
+    assert np.all(oracle.safe_mask(lcb2) <= S)
+    assert np.all(lcb2 <= lcb + 1e-15) and np.all(ucb2 >= ucb - 1e-15)
+    if not (S.any() and Z_all.any()):
+        return
+    # a larger Lipschitz constant shrinks every reach radius: expander and target sets can only shrink
+    L1 = np.full(G, max(1e-3, oracle.lipschitz_constant(pts, ds, G - 1)))
+    e1 = oracle.expander_lipschitz(pts, S, Z_all, ucb, v, L1)
+    e2 = oracle.expander_lipschitz(pts, S, Z_all, ucb, v, L1 * 3.0)
+    t1 = oracle.goose_target(pts, S, Z_all, ucb, lcb, L1)
+    t2 = oracle.goose_target(pts, S, Z_all, ucb, lcb, L1 * 3.0)
+    for c in range(G - 1):
+        assert np.all(e2["masks"][c] <= e1["masks"][c]) and np.all(e1["masks"][c] <= S)
+        assert np.all(t2["masks"][c] <= t1["masks"][c]) and np.all(t1["masks"][c] <= Z_all)
+    # an expander exists for constraint c iff a target exists for it (both say: some (x, z) pair passes the test)
+    for c in range(G - 1):
+        assert e1["masks"][c].any() == t1["masks"][c].any()
+    # the chosen expander is the most uncertain member of the union, lowest index on ties
+    if e1["best_idx"] >= 0:
+        union = np.any(e1["masks"], axis=0)
+        assert v[e1["best_idx"], 0] == v[union, 0].max()
+        assert e1["best_idx"] == np.flatnonzero(union & (v[:, 0] == v[union, 0].max()))[0]
+
+
+def test_arg_reductions_break_ties_towards_the_lowest_index(oracle):
+    vals = np.array([3.0, 1.0, 1.0, 5.0, 5.0, 1.0])
+    mask = np.array([True, False, True, True, True, True])
+    assert oracle.masked_argmin(vals, mask) == (2, 1.0)
+    assert oracle.masked_argmax(vals, mask) == (3, 5.0)
+    assert oracle.masked_argmin(vals, np.zeros(6, bool))[0] == -1 and oracle.masked_argmax(vals, np.zeros(6, bool))[0] == -1
