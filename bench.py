@@ -156,6 +156,19 @@ def cpu_extrapolate(s, N, pairs_full):
     return t_full
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core, so raise the
+    BLAS thread count back at run time.  Returns the number of BLAS threads in use."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        used = [i["num_threads"] for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(used) if used else n
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", n))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -163,7 +176,7 @@ def run_reference(args):
     (ds, lo, hi, pts, beta), wl_name = workload(args.workload)
     N = int(np.prod(pts))
     G = ds["Y_norm"].shape[1]
-    cores = os.cpu_count()
+    cores = use_all_host_threads()
     times, samples = [], []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -451,9 +464,10 @@ def run_ours(args):
     if world == 1 and not args.no_reference_configs:
         line["reference_configs"] = reference_configs(eng, torch)
     if not args.no_cpu_baseline and world == 1:
+        cpu_threads = use_all_host_threads()
         s = cpu_sample_step(ds, lo, hi, pts, beta, args.mode)
         t_full = cpu_extrapolate(s, N, pairs)
-        line["cpu_baseline"] = {"value": pairs / t_full, "unit": "pair-evals/s", "cores": os.cpu_count(), "kind": "port",
+        line["cpu_baseline"] = {"value": pairs / t_full, "unit": "pair-evals/s", "cores": cpu_threads, "kind": "port",
                                 "ms_per_step_extrapolated": t_full * 1e3,
                                 "sample": f"{s['n_points']} random grid points (posterior+sets) and {s['pairs']} pair-evals "
                                           f"timed on the host, extrapolated linearly to the full step"}

@@ -33,6 +33,11 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     assert _run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--workload", "c4s", "--steps", "1",
                  "--warmup", "0"], env) == []
+    # rank 0 under torchrun: OMP_NUM_THREADS=1 is imposed on the workers, the CPU arm still uses every host core
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    lines = _run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--workload", "c4s", "--steps", "1",
+                  "--warmup", "0"], env)
+    assert len(lines) == 1 and json.loads(lines[0])["cpu_baseline"]["cores"] == os.cpu_count()
 
 
 def test_our_arm_refuses_to_run_without_a_gpu():
