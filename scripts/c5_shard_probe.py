@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import sbo_b200
-from sbo_b200 import workloads, _capi as capi
+from sbo_b200 import workloads
 from oracle import gp_oracle as O
 
 ap = argparse.ArgumentParser()

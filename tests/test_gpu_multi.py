@@ -1,7 +1,6 @@
 """GPU, >= 2 devices (skipped otherwise): the sharded step over NCCL returns exactly the single-GPU result.
 Launched the way the driver launches bench.py: torch.distributed.run, one rank per GPU."""
 import json
-import os
 import subprocess
 import sys
 
