@@ -11,8 +11,9 @@ Outputs : tests/golden/c1_benoit.npz, tests/golden/c3_wor.npz -- realistic (X, Y
           oracle's own outputs (posterior at the points the reference's scripts print
           at, set sizes and chosen grid indices on the reference's 400x400 grid).
 
-The reference holds no known answers for this path (zero assertions, unseeded DE),
-so these are oracle outputs, not reference outputs: parity stays "unpinned".
+The reference holds no known answers for this path (zero assertions, unseeded DE), so these are oracle outputs
+kept as regression vectors.  The vectors that PIN the oracle are produced by the reference's own source:
+make_reference_vectors.py / make_reference_pairs.py / make_plant_vectors.py (ref_*.npz).
 """
 import os
 import pickle
