@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--no-lipschitz-steps", action="store_true", help="skip the reference-exact SafeOpt/GoOSE step times (extra key)")
     ap.add_argument("--no-reference-configs", action="store_true", help="skip the C1-C3 step times (extra key)")
-    ap.add_argument("--prune", type=int, default=0, help="1: also time the step with the exact z-side pruning (extra key)")
+    ap.add_argument("--prune", type=int, default=1, help="exact key-ordered tile pruning of the fantasy expander (default 1 = the library default; 0 = every pair)")
     return ap.parse_args()
 
 
@@ -303,6 +303,7 @@ def run_ours(args):
     if world > 1:
         eng.set_shard_cyclic(rank, world, 256)      # block-cyclic ownership balances |S| and |Z| over the ranks
     fantasy = args.mode == "fantasy"
+    eng.set_option("fantasy_prune", int(args.prune))
 
     def step(upload=True):
         """One acquisition step on this rank's shard.  Multi-GPU: collectives between the stages, issued on the
@@ -361,23 +362,6 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
     ex = res["expander"]
-    pruned = None
-    if args.prune and fantasy:
-        eng.set_option("fantasy_prune", 1)
-        with torch.cuda.stream(stream):
-            step()
-        barrier()
-        tp = []
-        for k in range(max(2, args.steps)):
-            flush.zero_(); barrier()
-            t0 = time.perf_counter()
-            with torch.cuda.stream(stream):
-                rp = step()
-            torch.cuda.synchronize(); tp.append(time.perf_counter() - t0)
-        eng.set_option("fantasy_prune", 0)
-        pruned = {"ms_per_step": float(np.mean(tp)) * 1e3, "pairs_evaluated": int(rp["expander"]["pairs_evaluated"]),
-                  "x_new_idx": int(rp["x_new_idx"]), "n_hit": int(rp["expander"]["n_hit"]),
-                  "note": "optional exact pruning (only optimistically-safe z are paired); same sets, not the headline"}
     # ---- the reference-exact (Lipschitz) acquisition steps on the same workload: SafeOpt and GoOSE step time ----
     lip = None
     if not args.no_lipschitz_steps:
@@ -457,8 +441,6 @@ def run_ours(args):
             "e2e": {"value": pairs / e2e_s, "unit": "pair-evals/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "peaks": {**peaks, "hbm_gbs": mp.get("hbm_gbs"), "bf16_tflops": mp.get("bf16_tflops")}}
-    if pruned is not None:
-        line["pruned"] = pruned
     if lip is not None:
         line["lipschitz_mode"] = lip
     if world == 1 and not args.no_reference_configs:

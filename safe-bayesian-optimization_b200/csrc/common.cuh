@@ -108,8 +108,8 @@ struct DevBuf {
 
 // state of the staged pair driver (pairs.cu)
 struct PairStage {
-  bool prepared = false, imported = false, counted = false;
-  int mode = 0, precision = 0, row_doubles = 0;
+  bool prepared = false, imported = false, counted = false, sorted = false;   // sorted: fantasy operands in key order (exact pruning)
+  int mode = 0, precision = 0, row_doubles = 0, count_scale = 1;
   double beta = 0.0;
   double L[SBO_MAX_G] = {0, 0, 0, 0, 0, 0, 0, 0};   // L[c] for constraint c+1
   long long nx_local = 0, nz_local = 0, nz_full = 0, nx_total = 0, pairs_evaluated = 0;   // nz_local <= nz_full when pruned
@@ -131,7 +131,7 @@ struct sbo_ctx {
   GridSpec gs{};
   DevBuf pts;
   // posterior (local shard)
-  bool have_post = false;
+  bool have_post = false, have_grad = false;   // have_grad: the last posterior accumulated the Lipschitz constants
   DevBuf mean, var, kx, lmax;
   int keep_v = 0;            // 0 none, 1 fp64, 2 fp32
   DevBuf vall;               // [(G-1)][count][npad] rows of V for the constraints
@@ -149,6 +149,7 @@ struct sbo_ctx {
   DevBuf nll_K, nll_in;                   // batched NLL (hyper-parameter fit): P x npad x npad factors, inputs/outputs
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
+  DevBuf key_x, key_z, perm_x, perm_z, sort_ws, tile_keys, item_mask, item_list;   // exact pruning of the fantasy expander
   PairStage ps;
   // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
   struct EvPair { cudaEvent_t a, b; int phase; };
@@ -157,9 +158,8 @@ struct sbo_ctx {
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // options
   int64_t opt_posterior_variant = 1;  // 0: FP64 SIMT register tiles, 1: FP64 tensor cores (DMMA m8n8k4)
-  int64_t opt_fantasy_prune = 0;      // 1: pair only the optimistically-safe part of Z (exact, see k_prune_unsafe)
+  int64_t opt_fantasy_prune = 1;      // 1 (default): exact key-ordered tile pruning of the fantasy expander (pairs.cu); 0: every pair
   long long n_unsafe_local = 0;
-  DevBuf m_prune;
   int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps;
                                      // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
   int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles

@@ -40,6 +40,8 @@ struct Params {
   int* counts;           // [nx]
   int* err;
   unsigned int* sched_counter;   // zeroed before every launch
+  const long long* item_list;    // feasible raster items in ascending order (exact pruning), or null = all n_items
+  const int* row_perm;           // sorted candidate slot -> row of `counts` (null = identity)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -296,7 +298,7 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int s2 = 0; uint32_t ph2 = 0;
       for (;;) {
         long long item = (long long)atomicAdd(p.sched_counter, 1u);
-        int v = (item < p.n_items) ? (int)item : -1;
+        int v = (item < p.n_items) ? (p.item_list ? (int)p.item_list[item] : (int)item) : -1;
         mbar_wait(bar_sempty(s2), ph2 ^ 1, p.err, 8);
         sched_items[s2] = v;
         mbar_arrive(bar_sfull(s2));
@@ -419,7 +421,7 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int cnt = 0;
 #pragma unroll
       for (int h = 0; h < NCH; ++h) cnt += __popc(bits[h]);
-      if (xrow < p.nx && cnt) atomicAdd(p.counts + xrow, cnt);
+      if (xrow < p.nx && cnt) atomicAdd(p.counts + (p.row_perm ? p.row_perm[xrow] : xrow), cnt);
     }
   }
   // ---- teardown
@@ -593,7 +595,7 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t peer_items = mapa_u32(smem_u32(const_cast<int*>(sched_items)), 1);
       for (;;) {
         long long item = (long long)atomicAdd(p.sched_counter, 1u);
-        int v = (item < p.n_items) ? (int)item : -1;
+        int v = (item < p.n_items) ? (p.item_list ? (int)p.item_list[item] : (int)item) : -1;
         mbar_wait_cl(bar_sempty(s2), ph2 ^ 1, p.err, 8);
         sched_items[s2] = v;
         st_cluster_u32(peer_items + 4 * s2, (uint32_t)v);
@@ -717,7 +719,7 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int cnt = 0;
 #pragma unroll
       for (int h = 0; h < NCH; ++h) cnt += __popc(bits[h]);
-      if (xrow < p.nx && cnt) atomicAdd(p.counts + xrow, cnt);
+      if (xrow < p.nx && cnt) atomicAdd(p.counts + (p.row_perm ? p.row_perm[xrow] : xrow), cnt);
     }
   }
   // ---- teardown: neither CTA may exit (or free TMEM) while the other can still signal it
@@ -803,7 +805,8 @@ static int make_map(sbo_ctx* ctx, CUtensorMap* map, const float* base, int rowle
 
 template <int BN, int D4, int EW>
 static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
-                  const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err) {
+                  const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err,
+                  const long long* item_list, long long n_list, const int* row_perm) {
   using C = Cfg<BN, D4>;
   CUtensorMap tmA, tmB;
   const int rowlen = split ? 2 * fc.npad : fc.npad;
@@ -815,15 +818,14 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
   p.nxt = (int)cdiv(nx, BM); p.nzt = (int)cdiv(nz, BN);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  p.n_items = cdiv(p.nxt, GX) * GX * (long long)p.nzt;
+  p.n_items = item_list ? n_list : cdiv(p.nxt, GX) * GX * (long long)p.nzt;
   SBO_REQUIRE(p.n_items < 2000000000LL, "too many tile pairs for one launch");
   p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
   p.sched_counter = (unsigned int*)(err + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc<BN, D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  p.item_list = item_list; p.row_perm = row_perm;
+  if (p.n_items == 0) return SBO_OK;
+  // per device and cheap: set before every launch (a process may hold contexts on several GPUs)
+  SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc<BN, D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int grid = (int)((p.n_items < sms) ? p.n_items : sms);
   k_fantasy_tc<BN, D4, EW><<<grid, 128 + 32 * EW, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
   SBO_LAUNCH_CHECK();
@@ -832,7 +834,8 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
 
 template <int D4, int EW>
 static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
-                   const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err) {
+                   const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err,
+                   const long long* item_list, long long n_list, const int* row_perm, int gx) {
   using C = Cfg2<D4>;
   CUtensorMap tmA, tmB;
   const int rowlen = split ? 2 * fc.npad : fc.npad;
@@ -845,17 +848,14 @@ static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int clusters = sms / 2;
-  // raster group: gx x tile pairs share each z tile; default keeps 4 z tiles in flight (as the 1-CTA kernel)
-  p.gx = ctx->opt_fantasy_gx > 0 ? (int)ctx->opt_fantasy_gx : (clusters + 3) / 4;
-  p.n_items = cdiv(p.nxt, p.gx) * p.gx * (long long)p.nzt;
+  p.gx = gx;
+  p.n_items = item_list ? n_list : cdiv(p.nxt, p.gx) * p.gx * (long long)p.nzt;
   SBO_REQUIRE(p.n_items < 2000000000LL, "too many tile pairs for one launch");
   p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
   p.sched_counter = (unsigned int*)(err + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc2<D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  p.item_list = item_list; p.row_perm = row_perm;
+  if (p.n_items == 0) return SBO_OK;
+  SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc2<D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int grid = 2 * (int)((p.n_items < clusters) ? p.n_items : clusters);
   k_fantasy_tc2<D4, EW><<<grid, 128 + 32 * EW, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
   SBO_LAUNCH_CHECK();
@@ -864,8 +864,43 @@ static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
 
 }  // namespace tc
 
+// keys of the exact pruning (pairs.cu): sorted key_x[nx] (max side), key_z[nz] (min side), slot -> counts row
+struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run; };
+// per tile of `tile` consecutive sorted entries: max (x side) or min (z side) of the keys
+__global__ void __launch_bounds__(256)
+k_tile_keys(long long n, int tile, int want_max, const double* __restrict__ key, double* __restrict__ out) {
+  __shared__ double red[8];
+  const long long t0 = (long long)blockIdx.x * tile;
+  double v = want_max ? -INFINITY : INFINITY;
+  for (long long t = t0 + threadIdx.x; t < t0 + tile && t < n; t += 256) v = want_max ? fmax(v, key[t]) : fmin(v, key[t]);
+  for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = want_max ? fmax(v, w) : fmin(v, w); }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) v = want_max ? fmax(v, red[w]) : fmin(v, red[w]);
+    out[blockIdx.x] = v;
+  }
+}
+// feasibility bitmask over the raster-ordered work items of the tcgen05 kernels (item -> (xt, zt) as item_coords*)
+__global__ void __launch_bounds__(256)
+k_item_mask(long long n_items, int gx, int nxt, int nzt, const double* __restrict__ qmax, const double* __restrict__ rmin,
+            uint32_t* __restrict__ words) {
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (item < n_items) {
+    const long long per_group = (long long)gx * nzt;
+    const int xg = (int)(item / per_group), r = (int)(item % per_group);
+    const int zt = r / gx, xt = xg * gx + r % gx;
+    ok = xt < nxt && rmin[zt] <= qmax[xt];
+  }
+  const uint32_t w = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && item < n_items) words[item >> 5] = w;
+}
+
+
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
-                   long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c) {
+                   long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c,
+                   const FantasyPruneArgs* pr) {
   const int d = fc.d, nc = fc.nc;
   const int D4 = d <= 4 ? 1 : 2;
   const int RS = 4 * D4 + 4;
@@ -897,10 +932,37 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   // outweighs the MMAs (short K) or carries 12-float records (d > 4)
   int variant = (int)ctx->opt_fantasy_variant;
   if (variant < 0) variant = 5 | ((fc.npad <= 256 || D4 == 2) ? 2 : 0);
+  // tile geometry of the chosen kernel and the raster of its work items
+  const bool two = (variant & 4) != 0;
+  const int tile_x = two ? 2 * tc::BM : tc::BM, tile_z = (two || (variant & 1)) ? 256 : 128;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int gx = two ? (ctx->opt_fantasy_gx > 0 ? (int)ctx->opt_fantasy_gx : (sms / 2 + 3) / 4) : tc::GX;
+  const int nxt = (int)cdiv(nx, tile_x), nzt = (int)cdiv(nz, tile_z);
+  const long long n_raster = cdiv(nxt, gx) * gx * (long long)nzt;
+  SBO_REQUIRE(n_raster < 2000000000LL, "too many tile pairs for one launch");
+  const long long* item_list = nullptr;
+  long long n_list = n_raster;
+  const int* row_perm = pr ? pr->row_perm : nullptr;
+  if (pr && pr->key_x && pr->key_z) {
+    // exact pruning: only (x tile, z tile) pairs with min key_z <= max key_x can hold a newly-safe pair
+    SBO_TRY(sbo_ensure(ctx, ctx->tile_keys, sizeof(double) * (size_t)(nxt + nzt)));
+    double* qmax = (double*)ctx->tile_keys.p; double* rmin = qmax + nxt;
+    k_tile_keys<<<nxt, 256, 0, ctx->stream>>>(nx, tile_x, 1, pr->key_x, qmax);
+    SBO_LAUNCH_CHECK();
+    k_tile_keys<<<nzt, 256, 0, ctx->stream>>>(nz, tile_z, 0, pr->key_z, rmin);
+    SBO_LAUNCH_CHECK();
+    SBO_TRY(sbo_ensure(ctx, ctx->item_mask, sizeof(uint32_t) * (size_t)cdiv(n_raster, 32)));
+    k_item_mask<<<(unsigned)cdiv(n_raster, 256), 256, 0, ctx->stream>>>(n_raster, gx, nxt, nzt, qmax, rmin, (uint32_t*)ctx->item_mask.p);
+    SBO_LAUNCH_CHECK();
+    SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->item_mask.p, n_raster, ctx->item_list, &n_list));
+    item_list = (const long long*)ctx->item_list.p;
+  }
+  if (pr && pr->items_run) *pr->items_run = n_list * (long long)tile_x * tile_z;   // pairs per constraint actually evaluated
   ev_end(ctx);            // record prep = phase 6
   ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)
-#define TC_LAUNCH(BN_, D4_, EW_) SBO_TRY((tc::launch<BN_, D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)))
-#define TC_LAUNCH2(D4_, EW_) SBO_TRY((tc::launch2<D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err)))
+#define TC_LAUNCH(BN_, D4_, EW_) SBO_TRY((tc::launch<BN_, D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err, item_list, n_list, row_perm)))
+#define TC_LAUNCH2(D4_, EW_) SBO_TRY((tc::launch2<D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err, item_list, n_list, row_perm, gx)))
   if (variant & 4) {            // 2-CTA pairs (cta_group::2), BN = 256
     if (D4 == 1) { if (variant & 2) TC_LAUNCH2(1, 8); else TC_LAUNCH2(1, 4); }
     else         { if (variant & 2) TC_LAUNCH2(2, 8); else TC_LAUNCH2(2, 4); }

@@ -244,7 +244,7 @@ int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const 
       return sbo_fail(ctx, SBO_ERR_NUMERIC, "K of GP " + std::to_string(g) + " is not positive definite at pivot " +
                                                 std::to_string(info[g] - 1));
   ctx->have_model = true;
-  ctx->have_post = ctx->have_sets = ctx->have_sets2 = false;
+  ctx->have_post = ctx->have_grad = ctx->have_sets = ctx->have_sets2 = false;
   return SBO_OK;
 }
 
@@ -362,6 +362,7 @@ int nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y,
       SBO_LAUNCH_CHECK();
     }
   }
+  SBO_CUDA(cudaFuncSetAttribute(k_nll_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (8192 + NB))));
   k_nll_finish<<<P, 256, sizeof(double) * (np + NB), ctx->stream>>>(n, np, K, yd, info, od);
   SBO_LAUNCH_CHECK();
   SBO_CUDA(cudaMemcpyAsync(nll, od, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));

@@ -311,13 +311,13 @@ k_export_v(int nc, int rowlen, long long n, long long vcount, const long long* _
 
 // imported rows (AoS) -> SoA payloads of the pair kernels
 __global__ void __launch_bounds__(256)
-k_import_rows(int d, int nc, long long n, PairConsts pc, const double* __restrict__ rows, double* __restrict__ coords,
+k_import_rows(int d, int nc, long long n, PairConsts pc, const int* __restrict__ perm, const double* __restrict__ rows, double* __restrict__ coords,
               double* __restrict__ ucb, double* __restrict__ thr, double* __restrict__ xn, double* __restrict__ ax,
               double* __restrict__ bx) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int RS = 2 * d + 3 * nc;
-  const double* r = rows + (size_t)t * RS;
+  const double* r = rows + (size_t)(perm ? perm[t] : t) * RS;        // slot t holds gathered candidate perm[t]
   for (int k = 0; k < d; ++k) { coords[(size_t)k * n + t] = r[k]; xn[(size_t)k * n + t] = r[d + nc + k]; }
   for (int c = 0; c < nc; ++c) {
     const double u = r[d + c];
@@ -335,14 +335,14 @@ k_import_rows(int d, int nc, long long n, PairConsts pc, const double* __restric
 // imported V rows [t][c][rowlen] -> GEMM operand layout Vx[c][nxp][rowlen], zero rows for t >= n
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_import_v(int nc, int rowlen, long long n, long long npadrows, const T* __restrict__ in, T* __restrict__ vout) {
+k_import_v(int nc, int rowlen, long long n, long long npadrows, const int* __restrict__ perm, const T* __restrict__ in, T* __restrict__ vout) {
   const long long t = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int c = blockIdx.y;
   if (t >= npadrows) return;
   const int lane = threadIdx.x & 31;
   T* o = vout + ((size_t)c * npadrows + t) * rowlen;
   if (t < n) {
-    const T* s = in + ((size_t)t * nc + c) * rowlen;
+    const T* s = in + ((size_t)(perm ? perm[t] : t) * nc + c) * rowlen;
     for (int k = lane; k < rowlen; k += 32) o[k] = s[k];
   } else {
     for (int k = lane; k < rowlen; k += 32) o[k] = (T)0;
@@ -385,23 +385,120 @@ k_fantasy_aux_z(GridSpec gs, ModelSpec ms, const long long* __restrict__ idx, lo
   }
 }
 
-// exact pruning of the z side of the fantasy expander: |cov(z,x)| <= sigma_z*sigma_x (posterior covariance is PSD)
-// gives mu'_c <= m_z + beta*sigma_z for every candidate x, so an unsafe z with ucb_c(z) < 0 for some constraint can
-// never become safe whatever x is observed.  Only the "optimistically safe" part of Z is paired.
+// ---------------------------------------------------------------------------------------------
+// Exact pruning of the fantasy expander (option fantasy_prune, default on).  The posterior covariance is PSD, so
+// |cov_c(z,x)| <= sigma_c(x) sigma_c(z); the updated bound  f(cov) = m_z + a_x cov - beta sqrt(s_z - b_x cov^2)  satisfies
+// f(-|cov|) <= f(|cov|) and is increasing for cov >= 0, hence for EVERY pair
+//     lcb'_c(z | x) <= m_z + beta sigma_z q_xc ,   q_xc = kappa - sqrt(1 - kappa),  kappa = sigma_x^2/(sigma_x^2 + sn2_c).
+// z can become safe through x only if  rho_zc := -m_zc/(beta sigma_zc) <= q_xc  for every constraint, which implies the
+// scalar test  key_z := max_c rho_zc  <=  key_x := max_c q_xc.  Candidates and unsafe points are ordered by their keys
+// (counting sort, 4096 bins), so the feasible (x tile, z tile) pairs form a staircase and every other tile pair is
+// skipped without changing any count (C4: 34 % of the tile pairs remain).  key_z > 1 can never be reached (q < 1):
+// those z are dropped altogether (the round-1 z-side pruning).  Slack: 1e-9 absolute on m_z (normalised units) and
+// 1e-6 on key_x, far above FP64 rounding of the bound and far below anything that matters for the pruning ratio.
+// ---------------------------------------------------------------------------------------------
+#define SORT_BINS 4096
+__device__ __forceinline__ int key_bin(double key) {
+  if (!(key >= -1.0)) return 0;                       // also NaN
+  if (key > 1.0) return SORT_BINS - 1;                // overflow bin: infeasible for every candidate
+  const int b = 1 + (int)((key + 1.0) * 0.5 * (SORT_BINS - 2));
+  return b > SORT_BINS - 2 ? SORT_BINS - 2 : b;
+}
 __global__ void __launch_bounds__(256)
-k_prune_unsafe(int G, long long count, const double* __restrict__ mean, const double* __restrict__ var, double beta,
-               double tol, ModelSpec ms, const uint32_t* __restrict__ unsafe_w, uint32_t* __restrict__ out_w) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
-  if (p < count && ((unsafe_w[p >> 5] >> (p & 31)) & 1u)) {
-    keep = true;
-    for (int i = 1; i < G; ++i) {
-      const double u = mean[(size_t)i * count + p] + beta * sqrt(var[(size_t)i * count + p]) * (1.0 + tol);
-      keep = keep && (u >= -tol * ms.Ystd[i]);
-    }
+k_key_z(int G, long long count, double beta, ModelSpec ms, const long long* __restrict__ idx, long long n,
+        const double* __restrict__ mean, const double* __restrict__ var, double* __restrict__ key) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long p = idx[t];
+  double k = -INFINITY;
+  for (int i = 1; i < G; ++i) {
+    const double num = -mean[(size_t)i * count + p] - 1e-9 * ms.Ystd[i];
+    const double den = beta * sqrt(var[(size_t)i * count + p]);
+    const double rho = (den > 0.0) ? num / den : (num > 0.0 ? INFINITY : -INFINITY);
+    k = fmax(k, rho);
   }
-  const uint32_t w = __ballot_sync(0xffffffffu, keep);
-  if ((threadIdx.x & 31) == 0 && p < count) out_w[p >> 5] = w;
+  key[t] = k;
+}
+// key_x from the gathered candidate rows [coords d | ucb nc | xn d | a nc | b nc]: kappa_c = 1 - sn2_c * b_c
+__global__ void __launch_bounds__(256)
+k_key_x(int d, int nc, long long n, FantasyConsts fc, const double* __restrict__ rows, double* __restrict__ key) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double* r = rows + (size_t)t * (2 * d + 3 * nc);
+  double k = -INFINITY;
+  for (int c = 0; c < nc; ++c) {
+    const double kap = fmin(fmax(1.0 - fc.sn2[c] * r[2 * d + 2 * nc + c], 0.0), 1.0);
+    k = fmax(k, kap - sqrt(1.0 - kap));
+  }
+  key[t] = k + 1e-6;
+}
+__global__ void __launch_bounds__(256)
+k_sort_hist(long long n, const double* __restrict__ key, int* __restrict__ hist) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) atomicAdd(hist + key_bin(key[t]), 1);
+}
+// one CTA: exclusive scan of the SORT_BINS counters into cursor[]; total[0] = n, total[1] = entries below the overflow bin
+__global__ void __launch_bounds__(1024) k_sort_scan(const int* __restrict__ hist, int* __restrict__ cursor, long long* __restrict__ total) {
+  __shared__ int wsum[32];
+  constexpr int PER = SORT_BINS / 1024;
+  int v[PER], s = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { v[i] = hist[threadIdx.x * PER + i]; s += v[i]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+    wsum[lane] = wi - w;
+    if (lane == 31) total[0] = wi;
+  }
+  __syncthreads();
+  int run = wsum[warp] + incl - s;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { cursor[threadIdx.x * PER + i] = run; run += v[i]; }
+  if (threadIdx.x == 1023) total[1] = run - v[PER - 1];     // start of the overflow bin
+}
+// perm[sorted slot] = original position (order inside a bin is arbitrary: no result depends on it)
+__global__ void __launch_bounds__(256)
+k_sort_scatter(long long n, const double* __restrict__ key, int* __restrict__ cursor, int* __restrict__ perm) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) perm[atomicAdd(cursor + key_bin(key[t]), 1)] = (int)t;
+}
+__global__ void __launch_bounds__(256)
+k_permute_idx(long long n, const int* __restrict__ perm, const long long* __restrict__ in, long long* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = in[perm[t]];
+}
+__global__ void __launch_bounds__(256)
+k_permute_key(long long n, const int* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = in[perm[t]];
+}
+// counting sort of n keys: perm_out[sorted slot] = original position; n_below = entries with key <= 1
+static int sort_by_key(sbo_ctx* ctx, long long n, const double* key, DevBuf& perm_buf, long long* n_below) {
+  SBO_REQUIRE(n < 2000000000LL, "too many points to sort");
+  SBO_TRY(sbo_ensure(ctx, ctx->sort_ws, sizeof(int) * 2 * SORT_BINS + 2 * sizeof(long long)));
+  SBO_TRY(sbo_ensure(ctx, perm_buf, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+  int* hist = (int*)ctx->sort_ws.p; int* cursor = hist + SORT_BINS; long long* total = (long long*)(cursor + SORT_BINS);
+  SBO_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * SORT_BINS, ctx->stream));
+  k_sort_hist<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, key, hist);
+  SBO_LAUNCH_CHECK();
+  k_sort_scan<<<1, 1024, 0, ctx->stream>>>(hist, cursor, total);
+  SBO_LAUNCH_CHECK();
+  k_sort_scatter<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(n, key, cursor, (int*)perm_buf.p);
+  SBO_LAUNCH_CHECK();
+  if (n_below) {
+    long long h[2];
+    SBO_CUDA(cudaMemcpyAsync(h, total, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_below = h[1];
+  }
+  return SBO_OK;
 }
 
 // per-element results -> bitmask words of the local shard (one mask per constraint)
@@ -449,12 +546,30 @@ k_fantasy_f64(FantasyConsts fc, long long nx, long long nz, long long nxp, long 
               const double* __restrict__ Vx, const double* __restrict__ Vz,
               const double* __restrict__ xn, const double* __restrict__ ax, const double* __restrict__ bx,
               const double* __restrict__ zn, const double* __restrict__ mz, const double* __restrict__ sz,
-              int* __restrict__ counts) {
+              int* __restrict__ counts, const double* __restrict__ key_x, const double* __restrict__ key_z,
+              const int* __restrict__ row_perm, unsigned long long* __restrict__ pair_counter) {
   __shared__ double As[FK][FB + 1];   // z rows
   __shared__ double Bs[FK][FB + 1];   // x rows
   __shared__ int cnt[16][FB];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long zb = (long long)blockIdx.x * FB, xb = (long long)blockIdx.y * FB;
+  if (key_x) {   // exact pruning (see k_key_z): no pair of this block can become safe when min key_z > max key_x
+    bool reach = false;
+    if (tid < FB) {
+      const double kx = (xb + tid < nx) ? key_x[xb + tid] : -INFINITY;
+      double qm = kx;
+      for (int o = 16; o > 0; o >>= 1) qm = fmax(qm, __shfl_xor_sync(0xffffffffu, qm, o));
+      const double kz = (zb + tid < nz) ? key_z[zb + tid] : INFINITY;
+      double rm = kz;
+      for (int o = 16; o > 0; o >>= 1) rm = fmin(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+      As[0][tid] = qm; Bs[0][tid] = rm;
+    }
+    __syncthreads();
+    reach = fmin(Bs[0][0], Bs[0][32]) <= fmax(As[0][0], As[0][32]);
+    __syncthreads();
+    if (!reach) return;
+  }
+  if (tid == 0 && pair_counter) atomicAdd(pair_counter, (unsigned long long)FB * FB);
   const int np = fc.npad;
   unsigned okmask = 0xffffu;   // bit i*4+j
   double zc[4][D], xc[4][D];
@@ -533,12 +648,14 @@ k_fantasy_f64(FantasyConsts fc, long long nx, long long nz, long long nxp, long 
 #pragma unroll
     for (int t = 0; t < 16; ++t) s += cnt[t][tid];
     const long long xi = xb + tid;
-    if (xi < nx && s) atomicAdd(counts + xi, s);
+    if (xi < nx && s) atomicAdd(counts + (row_perm ? row_perm[xi] : xi), s);
   }
 }
 
+struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run; };
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
-                   long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c);
+                   long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c,
+                   const FantasyPruneArgs* pr);
 
 // =============================================================================================
 // staged host driver
@@ -574,17 +691,25 @@ int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const doub
   ps.nz_full = 0;
   if (nc > 0) {
     SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_safe.p, count, ctx->xs_idx, &nx));
-    if (mode == SBO_MODE_FANTASY && ctx->opt_fantasy_prune) {
-      const long long nw = mask_words(ctx);
-      SBO_TRY(sbo_ensure(ctx, ctx->m_prune, sizeof(uint32_t) * nw));
-      k_prune_unsafe<<<(unsigned)cdiv(count, 256), 256, 0, ctx->stream>>>(ms.G, count, (const double*)ctx->mean.p, (const double*)ctx->var.p,
-                                                                         beta, 1e-6, ms, (const uint32_t*)ctx->m_unsafe.p, (uint32_t*)ctx->m_prune.p);
+    SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
+    ps.nz_full = nz;
+    if (mode == SBO_MODE_FANTASY && ctx->opt_fantasy_prune && nz > 0) {
+      // order the unsafe points by key_z = max_c rho_zc and drop those no candidate can reach (key_z > 1)
+      SBO_TRY(sbo_ensure(ctx, ctx->key_z, sizeof(double) * (size_t)nz * 2));
+      double* kz = (double*)ctx->key_z.p;
+      k_key_z<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(ms.G, count, beta, ms, (const long long*)ctx->zs_idx.p, nz,
+                                                               (const double*)ctx->mean.p, (const double*)ctx->var.p, kz + nz);
       SBO_LAUNCH_CHECK();
-      SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_prune.p, count, ctx->zs_idx, &nz));
-      ps.nz_full = ctx->n_unsafe_local;
-    } else {
-      SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->m_unsafe.p, count, ctx->zs_idx, &nz));
-      ps.nz_full = nz;
+      long long keep = nz;
+      SBO_TRY(sort_by_key(ctx, nz, kz + nz, ctx->perm_z, &keep));
+      SBO_TRY(sbo_ensure(ctx, ctx->scan_b, sizeof(long long) * (size_t)nz));
+      k_permute_idx<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(nz, (const int*)ctx->perm_z.p, (const long long*)ctx->zs_idx.p, (long long*)ctx->scan_b.p);
+      SBO_LAUNCH_CHECK();
+      k_permute_key<<<(unsigned)cdiv(nz, 256), 256, 0, ctx->stream>>>(nz, (const int*)ctx->perm_z.p, kz + nz, kz);
+      SBO_LAUNCH_CHECK();
+      std::swap(ctx->zs_idx, ctx->scan_b);          // zs_idx is now in key order; kz[0..nz) the sorted keys
+      nz = keep;
+      ps.sorted = true;
     }
   }
   ps.nx_local = nx; ps.nz_local = nz;
@@ -663,7 +788,21 @@ int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const vo
   double* xc = (double*)ctx->xs_pay.p; double* ucb = xc + (size_t)d * n_total; double* thr = ucb + (size_t)nc * n_total;
   double* xn = (double*)ctx->aux_x.p; double* ax = xn + (size_t)d * n_total; double* bx = ax + (size_t)nc * n_total;
   ev_begin(ctx, 6);
-  k_import_rows<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(d, nc, n_total, pc, (const double*)rows_dev, xc, ucb, thr, xn, ax, bx);
+  const int* xperm = nullptr;
+  if (ps.sorted) {   // order ALL candidates by key_x = max_c q_xc (+ slack): see the pruning note above
+    FantasyConsts fk{};
+    fk.nc = nc;
+    for (int c = 0; c < nc; ++c) fk.sn2[c] = ms.sn2[c + 1];
+    SBO_TRY(sbo_ensure(ctx, ctx->key_x, sizeof(double) * (size_t)n_total * 2));
+    double* kx = (double*)ctx->key_x.p;
+    k_key_x<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(d, nc, n_total, fk, (const double*)rows_dev, kx + n_total);
+    SBO_LAUNCH_CHECK();
+    SBO_TRY(sort_by_key(ctx, n_total, kx + n_total, ctx->perm_x, nullptr));
+    k_permute_key<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(n_total, (const int*)ctx->perm_x.p, kx + n_total, kx);
+    SBO_LAUNCH_CHECK();
+    xperm = (const int*)ctx->perm_x.p;
+  }
+  k_import_rows<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(d, nc, n_total, pc, xperm, (const double*)rows_dev, xc, ucb, thr, xn, ax, bx);
   SBO_LAUNCH_CHECK();
   if (ps.mode == SBO_MODE_FANTASY) {
     SBO_REQUIRE(vrows_dev != nullptr, "null V import buffer");
@@ -671,9 +810,9 @@ int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const vo
     const long long nxp = cdiv(n_total, 256) * 256;
     SBO_TRY(sbo_ensure(ctx, ctx->vx, v_elem_size(ctx) * (size_t)nc * nxp * rowlen));
     if (ps.precision == SBO_PREC_FP64)
-      k_import_v<double><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, n_total, nxp, (const double*)vrows_dev, (double*)ctx->vx.p);
+      k_import_v<double><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, n_total, nxp, xperm, (const double*)vrows_dev, (double*)ctx->vx.p);
     else
-      k_import_v<float><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, n_total, nxp, (const float*)vrows_dev, (float*)ctx->vx.p);
+      k_import_v<float><<<dim3((unsigned)cdiv(nxp, 8), nc), 256, 0, ctx->stream>>>(nc, rowlen, n_total, nxp, xperm, (const float*)vrows_dev, (float*)ctx->vx.p);
     SBO_LAUNCH_CHECK();
   }
   ev_end(ctx);
@@ -732,21 +871,28 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     const long long nxp = cdiv(nx, 256) * 256, nzp = cdiv(nz, 256) * 256;
     const double* zn = (const double*)ctx->aux_z.p; const double* mz = zn + (size_t)d * nz; const double* sz = mz + (size_t)nc * nz;
     int* cnt = (int*)result_dev;
+    const double* key_x = ps.sorted ? (const double*)ctx->key_x.p : nullptr;
+    const double* key_z = ps.sorted ? (const double*)ctx->key_z.p : nullptr;
+    const int* row_perm = ps.sorted ? (const int*)ctx->perm_x.p : nullptr;
     if (ps.precision == SBO_PREC_FP64) {
       dim3 grid((unsigned)cdiv(nz, FB), (unsigned)cdiv(nx, FB));
       SBO_REQUIRE(grid.y <= 65535, "too many candidates for the FP64 fantasy kernel");
       ev_begin(ctx, 4);
-#define FL(DD) k_fantasy_f64<DD><<<grid, 256, 0, ctx->stream>>>(fc, nx, nz, nxp, nzp, (const double*)ctx->vx.p, (const double*)ctx->vz.p, xn, ax, bx, zn, mz, sz, cnt)
+#define FL(DD) k_fantasy_f64<DD><<<grid, 256, 0, ctx->stream>>>(fc, nx, nz, nxp, nzp, (const double*)ctx->vx.p, (const double*)ctx->vz.p, xn, ax, bx, zn, mz, sz, cnt, key_x, key_z, row_perm, ctr)
       switch (d) { case 1: FL(1); break; case 2: FL(2); break; case 3: FL(3); break; case 4: FL(4); break;
                    case 5: FL(5); break; case 6: FL(6); break; case 7: FL(7); break; default: FL(8); break; }
 #undef FL
       SBO_LAUNCH_CHECK();
+      ps.counted = true;          // pairs evaluated = ctr[0] * nc (read back in finish)
+      ps.count_scale = nc;
     } else {   // record prep is logged as phase 6, the GEMM kernel as phase 4 (begun inside)
+      long long run_pairs = nx * nz;
+      FantasyPruneArgs pr{key_x, key_z, row_perm, &run_pairs};
       SBO_TRY(fantasy_tc_run(ctx, fc, ps.precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p,
-                             (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt));
+                             (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt, &pr));
+      ps.pairs_evaluated = (ps.sorted ? run_pairs : nx * nz) * nc;
     }
     ev_end(ctx);
-    ps.pairs_evaluated = nx * nz * nc;
   }
   return SBO_OK;
 }
@@ -803,8 +949,9 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
   SBO_CUDA(cudaStreamSynchronize(ctx->stream));
   ev_collect(ctx);
   out->n_hit = (int64_t)h[1];
-  if (ps.counted) out->pairs_evaluated = (int64_t)h[0] < out->pairs_algorithmic ? (int64_t)h[0] : out->pairs_algorithmic;
+  if (ps.counted) out->pairs_evaluated = (int64_t)h[0] * ps.count_scale;
   else out->pairs_evaluated = ps.pairs_evaluated;
+  if (out->pairs_evaluated > out->pairs_algorithmic) out->pairs_evaluated = out->pairs_algorithmic;
   if (!have) return SBO_OK;
   // per-constraint arg-reduction, then first-best across constraints (SafeOpt.py:120-122 / GoOSE.py:110-112)
   const double keep5 = ctx->phase_ms[5];

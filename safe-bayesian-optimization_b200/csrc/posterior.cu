@@ -380,14 +380,11 @@ static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, i
                           long long out_ld, int keep_v, void* vall, long long v_count) {
   if (ctx->opt_posterior_variant == 1) {   // FP64 tensor-core (DMMA) kernel
     dim3 grid((unsigned)(P / DV_BP), (unsigned)ctx->ms.G);
-    static bool attr = false;
-    if (!attr) {
-      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
-      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
-      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
-      SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
-      attr = true;
-    }
+    // the attribute is per device and a process may hold contexts on several GPUs: set it before every launch
+    SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+    SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+    SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
+    SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
     if (keep_v == 1) k_solve_var_dmma<1><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
     else if (keep_v == 2) k_solve_var_dmma<2><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
     else if (keep_v == 3) k_solve_var_dmma<3><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
@@ -452,6 +449,7 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   }
   if (keep_v && ms.G > 1) ctx->keep_v = keep_v;
   ctx->have_post = true;
+  ctx->have_grad = with_grad != 0;
   ctx->have_sets = ctx->have_sets2 = false;
   return SBO_OK;
 }

@@ -150,6 +150,105 @@ k_sets_pass2(long long count, GridSpec gs, const double* __restrict__ mean, cons
   if (threadIdx.x == 0) part[blockIdx.x] = Pass2Partial{a.v, a.i, nm};
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised K2 (count % 4 == 0): persistent grid-stride CTAs, 4 consecutive points per thread read with 128-bit
+// loads (2 x double2 per GP array), every load of a tile issued before the first use; one nibble of mask bits per
+// thread, assembled into words by three xor-shuffles inside groups of 8 lanes.  HBM-bound: 16*G bytes per point.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld4(const double* __restrict__ p, double (&v)[4]) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ uint32_t nibble_to_word(uint32_t nib, int lane) {
+  uint32_t w = nib << (4 * (lane & 7));
+  w |= __shfl_xor_sync(0xffffffffu, w, 1);
+  w |= __shfl_xor_sync(0xffffffffu, w, 2);
+  w |= __shfl_xor_sync(0xffffffffu, w, 4);
+  return w;   // identical in the 8 lanes of a group
+}
+
+template <int G>
+__global__ void __launch_bounds__(ST)
+k_sets_pass1_v4(long long count, GridSpec gs, const double* __restrict__ mean, const double* __restrict__ var,
+                double beta, int rule, int strict, uint32_t* __restrict__ safe_w, uint32_t* __restrict__ unsafe_w,
+                SetsPartial* __restrict__ part) {
+  __shared__ ArgVal sm_av[ST / 32];
+  __shared__ long long sm_ll[ST / 32];
+  const int lane = threadIdx.x & 31;
+  ArgVal u{INFINITY, SBO_IDX_NONE}, l{INFINITY, SBO_IDX_NONE};
+  long long ns = 0, nu = 0;
+  for (long long base = (long long)blockIdx.x * (4 * ST); base < count; base += (long long)gridDim.x * (4 * ST)) {
+    const long long p = base + 4 * threadIdx.x;
+    uint32_t sb = 0, ub = 0;
+    if (p < count) {
+      double m[G][4], v[G][4];
+#pragma unroll
+      for (int i = 0; i < G; ++i) { ld4(mean + (size_t)i * count + p, m[i]); ld4(var + (size_t)i * count + p, v[i]); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bool safe = true, all_le = true, any_lt = false;
+#pragma unroll
+        for (int i = 1; i < G; ++i) {
+          const double lcb = lcb_of(m[i][j], v[i][j], beta);                                  // SafeOpt.py:40-45
+          safe = safe && (strict ? (lcb > 0.0) : (lcb >= 0.0));
+          all_le = all_le && (lcb <= 0.0);
+          any_lt = any_lt || (lcb < 0.0);
+        }
+        const bool unsafe = (G > 1) && (rule == SBO_UNSAFE_ALL ? all_le : any_lt);
+        if (safe) {
+          const long long gi = shard_global(gs, p + j);
+          u = argmin2(u, ArgVal{ucb_of(m[0][j], v[0][j], beta), gi});
+          l = argmin2(l, ArgVal{lcb_of(m[0][j], v[0][j], beta), gi});
+          sb |= 1u << j; ++ns;
+        }
+        if (unsafe) { ub |= 1u << j; ++nu; }
+      }
+    }
+    const uint32_t ws = nibble_to_word(sb, lane), wu = nibble_to_word(ub, lane);
+    if ((lane & 7) == 0 && p < count) { safe_w[p >> 5] = ws; unsafe_w[p >> 5] = wu; }
+  }
+  u = block_argmin(u, sm_av);
+  l = block_argmin(l, sm_av);
+  ns = block_sum_ll(ns, sm_ll);
+  nu = block_sum_ll(nu, sm_ll);
+  if (threadIdx.x == 0) part[blockIdx.x] = SetsPartial{u.v, u.i, l.v, l.i, ns, nu};
+}
+
+__global__ void __launch_bounds__(ST)
+k_sets_pass2_v4(long long count, GridSpec gs, const double* __restrict__ mean, const double* __restrict__ var,
+                double beta, double min_ucb0, const uint32_t* __restrict__ safe_w, uint32_t* __restrict__ min_w,
+                Pass2Partial* __restrict__ part) {
+  __shared__ ArgVal sm_av[ST / 32];
+  __shared__ long long sm_ll[ST / 32];
+  const int lane = threadIdx.x & 31;
+  ArgVal a{-INFINITY, SBO_IDX_NONE};
+  long long nm = 0;
+  for (long long base = (long long)blockIdx.x * (4 * ST); base < count; base += (long long)gridDim.x * (4 * ST)) {
+    const long long p = base + 4 * threadIdx.x;
+    uint32_t mb = 0;
+    if (p < count) {
+      const uint32_t sb = (safe_w[p >> 5] >> (p & 31)) & 0xfu;
+      if (sb) {                                      // the objective's arrays are read only where a point is safe
+        double m[4], v[4];
+        ld4(mean + p, m); ld4(var + p, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (((sb >> j) & 1u) && lcb_of(m[j], v[j], beta) <= min_ucb0) {        // SafeOpt.py:62
+            mb |= 1u << j; ++nm;
+            a = argmax2(a, ArgVal{v[j], shard_global(gs, p + j)});               // SafeOpt.py:55,65
+          }
+      }
+    }
+    const uint32_t wm = nibble_to_word(mb, lane);
+    if ((lane & 7) == 0 && p < count) min_w[p >> 5] = wm;
+  }
+  a = block_argmax(a, sm_av);
+  nm = block_sum_ll(nm, sm_ll);
+  if (threadIdx.x == 0) part[blockIdx.x] = Pass2Partial{a.v, a.i, nm};
+}
+
 __global__ void __launch_bounds__(ST) k_sets_final2(const Pass2Partial* __restrict__ part, int nblocks, SetsDeviceResult* __restrict__ res) {
   __shared__ ArgVal sm_av[ST / 32];
   __shared__ long long sm_ll[ST / 32];
@@ -229,11 +328,30 @@ __global__ void __launch_bounds__(256) k_scan_blocksum(const uint32_t* __restric
   s = block_sum_ll(s, sm_ll);
   if (threadIdx.x == 0) bsum[blockIdx.x] = s;
 }
-__global__ void k_scan_serial(long long* __restrict__ bsum, int nblocks, long long* __restrict__ total) {
-  // single thread: nblocks <= a few thousand
-  long long run = 0;
-  for (int b = 0; b < nblocks; ++b) { const long long v = bsum[b]; bsum[b] = run; run += v; }
-  *total = run;
+// exclusive scan of the block sums by ONE CTA: every thread scans a contiguous run, the run totals are scanned
+// with warp shuffles (nblocks is count/32768: 512 at C5, so one CTA is enough)
+__global__ void __launch_bounds__(1024) k_scan_blocks(long long* __restrict__ bsum, int nblocks, long long* __restrict__ total) {
+  __shared__ long long wsum[32];
+  const int per = (nblocks + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(nblocks, b0 + per);
+  long long s = 0;
+  for (int b = b0; b < b1; ++b) s += bsum[b];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = wsum[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+    wsum[lane] = wi - w;
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  long long run = wsum[warp] + incl - s;
+  for (int b = b0; b < b1; ++b) { const long long v = bsum[b]; bsum[b] = run; run += v; }
 }
 __global__ void __launch_bounds__(32) k_scan_scatter(const uint32_t* __restrict__ mask, long long nwords, long long count,
                                                      const long long* __restrict__ boff, long long* __restrict__ out) {
@@ -266,7 +384,7 @@ int compact_mask(sbo_ctx* ctx, const uint32_t* mask_dev, long long count, DevBuf
   long long* bsum = (long long*)ctx->scan_a.p;
   k_scan_blocksum<<<nblocks, 256, 0, ctx->stream>>>(mask_dev, nwords, count, bsum);
   SBO_LAUNCH_CHECK();
-  k_scan_serial<<<1, 1, 0, ctx->stream>>>(bsum, nblocks, bsum + nblocks);
+  k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(bsum, nblocks, bsum + nblocks);
   SBO_LAUNCH_CHECK();
   long long total = 0;
   SBO_CUDA(cudaMemcpyAsync(&total, bsum + nblocks, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -298,6 +416,14 @@ uint32_t* mask_ptr(sbo_ctx* ctx, int mask_kind, int which) {
   return nullptr;
 }
 
+// persistent grid of the vectorised set kernels: 8 CTAs of 256 threads per SM (one wave), never more CTAs than tiles
+static int sets_grid(sbo_ctx* ctx, long long count) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const long long tiles = cdiv(count, 4 * ST);
+  return (int)(tiles < (long long)sms * 8 ? tiles : (long long)sms * 8);
+}
+
 static void fill_result(const SetsDeviceResult& r, sbo_sets_result* out) {
   out->n_safe = r.n_safe; out->n_unsafe = r.n_unsafe; out->n_min = r.n_min;
   out->min_ucb0 = r.min_ucb; out->min_ucb0_idx = r.min_ucb_i;
@@ -310,7 +436,8 @@ int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result*
   SBO_REQUIRE(rule == SBO_UNSAFE_ALL || rule == SBO_UNSAFE_ANY, "bad unsafe rule");
   const long long count = ctx->gs.count;
   const long long nw = mask_words(ctx);
-  const int nblocks = (int)cdiv(count, ST);
+  const bool vec = (count % 4 == 0);
+  const int nblocks = vec ? sets_grid(ctx, count) : (int)cdiv(count, ST);
   SBO_TRY(sbo_ensure(ctx, ctx->m_safe, sizeof(uint32_t) * nw));
   SBO_TRY(sbo_ensure(ctx, ctx->m_unsafe, sizeof(uint32_t) * nw));
   SBO_TRY(sbo_ensure(ctx, ctx->m_min, sizeof(uint32_t) * nw));
@@ -319,6 +446,13 @@ int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result*
   ev_reset(ctx, 3);
   ev_begin(ctx, 3);
   SBO_CUDA(cudaMemsetAsync(ctx->result.p, 0, sizeof(SetsDeviceResult), ctx->stream));
+#define P1V(GG) k_sets_pass1_v4<GG><<<nblocks, ST, 0, ctx->stream>>>(count, ctx->gs, (const double*)ctx->mean.p, (const double*)ctx->var.p, \
+      beta, rule, strict, (uint32_t*)ctx->m_safe.p, (uint32_t*)ctx->m_unsafe.p, (SetsPartial*)ctx->partials.p)
+  if (vec) {
+    switch (ctx->ms.G) { case 1: P1V(1); break; case 2: P1V(2); break; case 3: P1V(3); break; case 4: P1V(4); break;
+                         case 5: P1V(5); break; case 6: P1V(6); break; case 7: P1V(7); break; default: P1V(8); break; }
+  } else
+#undef P1V
   k_sets_pass1<<<nblocks, ST, 0, ctx->stream>>>(ctx->ms.G, count, ctx->gs, (const double*)ctx->mean.p,
                                                 (const double*)ctx->var.p, beta, rule, strict,
                                                 (uint32_t*)ctx->m_safe.p, (uint32_t*)ctx->m_unsafe.p,
@@ -343,9 +477,15 @@ int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result*
 int sets_pass2(sbo_ctx* ctx, double min_ucb0, sbo_sets_result* out) {
   SBO_REQUIRE(ctx->have_sets, "sbo_sets_pass2: call sbo_sets_pass1 first");
   const long long count = ctx->gs.count;
-  const int nblocks = (int)cdiv(count, ST);
+  const bool vec = (count % 4 == 0);
+  const int nblocks = vec ? sets_grid(ctx, count) : (int)cdiv(count, ST);
   SBO_TRY(sbo_ensure(ctx, ctx->partials, sizeof(SetsPartial) * (size_t)nblocks));   // >= Pass2Partial
   ev_begin(ctx, 3);
+  if (vec)
+    k_sets_pass2_v4<<<nblocks, ST, 0, ctx->stream>>>(count, ctx->gs, (const double*)ctx->mean.p, (const double*)ctx->var.p,
+                                                     ctx->beta, min_ucb0, (const uint32_t*)ctx->m_safe.p,
+                                                     (uint32_t*)ctx->m_min.p, (Pass2Partial*)ctx->partials.p);
+  else
   k_sets_pass2<<<nblocks, ST, 0, ctx->stream>>>(count, ctx->gs, (const double*)ctx->mean.p, (const double*)ctx->var.p,
                                                 ctx->beta, min_ucb0, (const uint32_t*)ctx->m_safe.p,
                                                 (uint32_t*)ctx->m_min.p, (Pass2Partial*)ctx->partials.p);

@@ -519,8 +519,13 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
     engine.set_grid(lo, hi, grid)
     m, v = engine.posterior(keep_v=keep_v)
     engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
-    ex = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
-    engine.set_option("fantasy_variant", -1)
+    ex = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)      # exact pruning on (the default)
+    engine.set_option("fantasy_prune", 0)                                             # every pair through the GEMM
+    try:
+        ex_all = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+    finally:
+        engine.set_option("fantasy_prune", 1)
+        engine.set_option("fantasy_variant", -1)
     pts = oracle.make_grid(lo, hi, grid)
     lcb, _ = oracle.bounds(m, v, beta)
     S, Z = oracle.safe_mask(lcb), oracle.unsafe_mask(lcb, rule)
@@ -539,10 +544,14 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
     scale = sf2max * (1.0 + gain)[None, :]
     w64 = oracle.fantasy_counts(pts, ds, beta, S, Z)[S]
     out = {"newly_safe_fp64": int(w64.sum())}
+    assert np.all(got <= ex_all["counts"][S]) and ex["pairs_evaluated"] <= ex_all["pairs_evaluated"]
+    # the pruning is exact: it can only remove pairs the lower precision wrongly counted
+    assert np.abs(got - w64).sum() <= np.abs(ex_all["counts"][S].astype(np.int64) - w64).sum()
     if precision == "tf32":
         wtf = oracle.fantasy_counts(pts, ds, beta, S, Z, dtype="tf32")[S]
         amb_impl = (margin <= IMPL_TOL * scale).sum(axis=0)
-        d1 = np.abs(got - wtf)
+        # (1) is a statement about the un-pruned kernel: the pruning removes TF32 false positives the bound refutes
+        d1 = np.abs(ex_all["counts"][S].astype(np.int64) - wtf)
         # the TF32-operand oracle decides on ITS margin; allow its own near-threshold pairs as well
         assert np.all(d1 <= amb_impl + (np.abs(wtf - w64) > 0) * 2 + 2), (int(d1.max()), int(amb_impl.max()))
         amb = (margin <= TF32_TOL * scale).sum(axis=0)
