@@ -13,8 +13,10 @@ two cost classes that scale differently, so that each is extrapolated by its own
                    Lipschitz mode: dot-form distance in raw space, ucb - L*sqrt(.) >= 0 (SafeOpt.py:85-88).
                    Cost is linear in the number of (x, z, constraint) triples  ->  scaled by pairs / pairs_sample.
 
-Dense kernels are OpenBLAS DGEMMs through NumPy; the element-wise epilogues run on torch CPU tensors (FP64, all host
-threads) because NumPy's are single-threaded.  Everything is FP64.
+Dense kernels are OpenBLAS DGEMMs through NumPy; the element-wise epilogues run in oracle/pair_epilogue.c (fused,
+OpenMP, all host threads; built by __graft_entry__.build()) because NumPy's are single-threaded multi-pass -- with it
+the pair test is DGEMM-bound.  If that library is not built the same epilogue runs on torch CPU tensors.  Everything
+is FP64.
 """
 from __future__ import annotations
 
@@ -23,6 +25,37 @@ import time
 import numpy as np
 
 from . import gp_oracle as O
+
+
+import ctypes as C
+import os
+
+_EPI = None
+
+
+def _epilogue_lib():
+    """oracle/_build/libpair_epilogue.so (gcc -fopenmp; oracle/Makefile), or None when it has not been built."""
+    global _EPI
+    if _EPI is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libpair_epilogue.so")
+        _EPI = False
+        if os.path.exists(path):
+            try:
+                lib = C.CDLL(path)
+                D, U8 = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+                lib.fantasy_epilogue.argtypes = [C.c_int64, C.c_int64, D, D, D, D, D, D, C.c_double, C.c_double, U8]
+                lib.lipschitz_epilogue.argtypes = [C.c_int64, C.c_int64, D, D, C.c_double, U8]
+                lib.fantasy_epilogue.restype = lib.lipschitz_epilogue.restype = None
+                lib.epilogue_set_threads.argtypes = [C.c_int]
+                lib.epilogue_set_threads(os.cpu_count() or 1)        # every host core (torchrun sets OMP_NUM_THREADS=1)
+                _EPI = lib
+            except OSError:
+                _EPI = False
+    return _EPI or None
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
 def _torch():
@@ -83,12 +116,13 @@ def pairs_fantasy(points, dso, beta, pp, xs, zs, block=2048):
     mu_n = pp["mean"] / dso["Y_std"]
     var_n = pp["var"] / dso["Y_std"] ** 2
     counts = np.zeros(xs.size, dtype=np.int64)
+    epi = _epilogue_lib()
     t0 = time.perf_counter()
     for xb0 in range(0, xs.size, block):
         xb = xs[xb0:xb0 + block]
         for zb0 in range(0, zs.size, block):
             zb = zs[zb0:zb0 + block]
-            ok = torch.ones((zb.size, xb.size), dtype=torch.bool)
+            ok = np.ones((zb.size, xb.size), dtype=np.uint8) if epi else torch.ones((zb.size, xb.size), dtype=torch.bool)
             for i in range(1, G):
                 ell, sf2, sn2 = O.unpack_hyper(dso["hypopt"][:, i], d)
                 sn2 = sn2 + O.EPS_F32
@@ -96,14 +130,21 @@ def pairs_fantasy(points, dso, beta, pp, xs, zs, block=2048):
                 B = xn[xb] / np.sqrt(ell)
                 dist = (A * A).sum(1)[:, None] + (B * B).sum(1)[None, :] - 2.0 * (A @ B.T)     # GP_Safe.py:119
                 acc = pp["V"][i - 1][zb] @ pp["V"][i - 1][xb].T                                # DGEMM, K = n
-                c = torch.from_numpy(dist).mul_(-0.5).exp_().mul_(sf2).sub_(torch.from_numpy(acc))
                 den = var_n[xb, i] + sn2
+                if epi:
+                    ax = np.ascontiguousarray(beta * np.sqrt(var_n[xb, i]) / den)
+                    bx = np.ascontiguousarray(1.0 / den)
+                    mz, sz = np.ascontiguousarray(mu_n[zb, i]), np.ascontiguousarray(var_n[zb, i])
+                    epi.fantasy_epilogue(zb.size, xb.size, _dp(dist), _dp(acc), _dp(mz), _dp(sz), _dp(ax), _dp(bx),
+                                         float(sf2), float(beta), ok.ctypes.data_as(C.POINTER(C.c_uint8)))
+                    continue
+                c = torch.from_numpy(dist).mul_(-0.5).exp_().mul_(sf2).sub_(torch.from_numpy(acc))
                 a = torch.from_numpy(beta * np.sqrt(var_n[xb, i]) / den)[None, :]
                 b = torch.from_numpy(1.0 / den)[None, :]
                 mu = torch.from_numpy(mu_n[zb, i])[:, None] + c * a
                 s2 = (torch.from_numpy(var_n[zb, i])[:, None] - c.mul_(c).mul_(b)).clamp_(min=0.0)
                 ok &= mu.sub_(s2.sqrt_().mul_(beta)) >= 0.0
-            counts[xb0:xb0 + xb.size] += ok.sum(dim=0).numpy()
+            counts[xb0:xb0 + xb.size] += ok.sum(axis=0, dtype=np.int64) if epi else ok.sum(dim=0).numpy()
     secs = time.perf_counter() - t0
     pairs = xs.size * zs.size * (G - 1)
     return counts, secs, pairs * (2.0 * n + 3 * d + 20)
@@ -114,26 +155,34 @@ def pairs_lipschitz(points, pp, L, xs, zs, G, block=4096):
     dot-form distance (GEMM-shaped, K = d).  Returns (hit flags (G-1, |xs|), seconds, flops)."""
     torch = _torch()
     d = points.shape[1]
-    hit = np.zeros((G - 1, xs.size), dtype=bool)
+    hit = np.zeros((G - 1, xs.size), dtype=np.uint8)
+    epi = _epilogue_lib()
     t0 = time.perf_counter()
     for xb0 in range(0, xs.size, block):
         xb = xs[xb0:xb0 + block]
         X = points[xb] + O.PAIR_OFFSET
         for zb0 in range(0, zs.size, block):
             Zp = points[zs[zb0:zb0 + block]]
-            d2 = (X * X).sum(1)[:, None] + (Zp * Zp).sum(1)[None, :] - 2.0 * (X @ Zp.T)
+            d2 = np.ascontiguousarray((X * X).sum(1)[:, None] + (Zp * Zp).sum(1)[None, :] - 2.0 * (X @ Zp.T))
+            if epi:
+                for i in range(1, G):
+                    h = np.ascontiguousarray(hit[i - 1, xb0:xb0 + xb.size])
+                    u = np.ascontiguousarray(pp["ucb"][xb, i])
+                    epi.lipschitz_epilogue(xb.size, Zp.shape[0], _dp(d2), _dp(u), float(L[i]), h.ctypes.data_as(C.POINTER(C.c_uint8)))
+                    hit[i - 1, xb0:xb0 + xb.size] = h
+                continue
             dist = torch.from_numpy(d2).clamp_(min=0.0).sqrt_()
             for i in range(1, G):
                 r = torch.from_numpy(pp["ucb"][xb, i] / L[i])[:, None]
-                hit[i - 1, xb0:xb0 + xb.size] |= (dist <= r).any(dim=1).numpy()
+                hit[i - 1, xb0:xb0 + xb.size] |= (dist <= r).any(dim=1).numpy().astype(np.uint8)
     secs = time.perf_counter() - t0
     pairs = xs.size * zs.size * (G - 1)
-    return hit, secs, pairs * (3.0 * d + 6)
+    return hit.astype(bool), secs, pairs * (3.0 * d + 6)
 
 
 def sample_step(ds, lo, hi, pts, beta, mode, n_points, n_x, n_z, seed=0):
-    """One bounded CPU step.  `n_points` grid points (a contiguous slab of the x_0-fastest grid starting at a seeded
-    offset, so that safe and unsafe points both occur), then the pair test for up to n_x safe x n_z unsafe of them."""
+    """One bounded CPU step.  `n_points` random grid points (seeded, without replacement; per-point work does not
+    depend on which points), then the pair test for up to n_x safe x n_z unsafe of them."""
     G = ds["Y_norm"].shape[1]
     d = len(pts)
     N = int(np.prod(pts))

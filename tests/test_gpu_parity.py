@@ -545,8 +545,6 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
     w64 = oracle.fantasy_counts(pts, ds, beta, S, Z)[S]
     out = {"newly_safe_fp64": int(w64.sum())}
     assert np.all(got <= ex_all["counts"][S]) and ex["pairs_evaluated"] <= ex_all["pairs_evaluated"]
-    # the pruning is exact: it can only remove pairs the lower precision wrongly counted
-    assert np.abs(got - w64).sum() <= np.abs(ex_all["counts"][S].astype(np.int64) - w64).sum()
     if precision == "tf32":
         wtf = oracle.fantasy_counts(pts, ds, beta, S, Z, dtype="tf32")[S]
         amb_impl = (margin <= IMPL_TOL * scale).sum(axis=0)
