@@ -160,7 +160,7 @@ int sbo_goose_target(sbo_ctx* ctx, double beta, const double* L /* G */, sbo_pai
 /* ---- the same pair stage in five steps, for a grid sharded over ranks ---------------
  * Every rank pairs ALL candidates x in S (gathered from all ranks) with ITS OWN unsafe points z:
  *   sbo_pairs_prepare     compact the local S and Z, build the local z-side operands
- *   sbo_pairs_export_dev  write the local candidates' rows [coords d | ucb G-1 | xn d | a G-1 | b G-1] (doubles,
+ *   sbo_pairs_export_dev  write the local candidates' rows [coords d | ucb G-1 | xn d | a G-1 | b G-1 | grid index] (doubles,
  *                         row_doubles per candidate) and, in fantasy mode, their V rows (vrow_bytes per
  *                         candidate) into caller-owned DEVICE buffers  -> all-gather them (NCCL)
  *   sbo_pairs_import_dev  hand the concatenation of all ranks' rows back (n_total candidates)
@@ -176,6 +176,20 @@ int sbo_pairs_export_dev(sbo_ctx* ctx, void* rows_dev, void* vrows_dev);
 int sbo_pairs_import_dev(sbo_ctx* ctx, int64_t n_total, const void* rows_dev, const void* vrows_dev);
 int sbo_pairs_run_dev(sbo_ctx* ctx, int goose, void* result_dev);
 int sbo_pairs_finish_dev(sbo_ctx* ctx, int goose, int64_t offset, const void* result_dev, sbo_pair_result* out, int32_t* counts);
+/* Sharded runs, Lipschitz mode (models/SafeOpt.py:85-124 with the grid split over ranks):
+ *   sbo_pairs_set_segments           (after prepare) how many candidates every rank exported, and this rank: the gathered
+ *                                    rows are put back into grid order inside the library (compact tiles for the exact
+ *                                    culling); results stay in the caller's gathered order.
+ *   sbo_mask_export_dev              copy a local bitmask into a caller-owned DEVICE buffer (zero padded to dst_words),
+ *                                    e.g. the unsafe mask for the all-gather north_star names (N/8 bytes in total).
+ *   sbo_pairs_set_global_unsafe_dev  hand the all-gathered local UNSAFE masks back (rank-major, words_per_rank each):
+ *                                    the SafeOpt expander then pairs THIS rank's share of the candidate tiles with ALL
+ *                                    unsafe points in grid order, so the per-candidate early exit and the tile culling
+ *                                    do the same work as on one GPU, divided by the number of ranks.  The per-candidate
+ *                                    hit flags are combined with the same all-reduce(max) as before. */
+int sbo_pairs_set_segments(sbo_ctx* ctx, int nranks, int rank, const int64_t* n_per_rank);
+int sbo_mask_export_dev(sbo_ctx* ctx, int mask_kind, int which, void* dst_dev, int64_t dst_words);
+int sbo_pairs_set_global_unsafe_dev(sbo_ctx* ctx, const void* gathered_words_dev, int64_t words_per_rank, int nranks);
 /* which = idx-1 (lipschitz/target: one mask per constraint) ; fantasy: which = 0 */
 #define SBO_MASK_EXPANDER 4
 #define SBO_MASK_TARGET   5
@@ -190,7 +204,9 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
  *   "posterior_variant"  1 (default) FP64 tensor cores (DMMA) | 0 FP64 SIMT register tiles
  *   "fantasy_variant"    -1 (default) auto | bit 0: 256-column z tiles, bit 1: 8 epilogue warps, bit 2: 2-CTA pairs
  *   "fantasy_gx"         x tile pairs per raster group of the 2-CTA GEMM (0 = default: a quarter of the clusters)
- *   "fantasy_prune"      1: pair only the optimistically-safe part of Z (exact; default 0)
+ *   "fantasy_prune"      1 (default): exact pruning of the fantasy expander -- candidates and unsafe points are ordered by the
+ *                        Cauchy-Schwarz keys of csrc/pairs.cu (k_key_x / k_key_z) and only tile pairs whose keys can meet
+ *                        are evaluated; FP64 counts are unchanged | 0: every pair goes through the GEMM
  *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
 /* ---- hyper-parameter fit:  GP.negative_loglikelihood  (GP_Safe.py:169-192), batched ------

@@ -79,6 +79,9 @@ SIGNATURES = {
     "sbo_pairs_export_dev": (C.c_int, [_P, _P, _P]),
     "sbo_pairs_import_dev": (C.c_int, [_P, C.c_int64, _P, _P]),
     "sbo_pairs_run_dev": (C.c_int, [_P, C.c_int, _P]),
+    "sbo_pairs_set_segments": (C.c_int, [_P, C.c_int, C.c_int, _I64]),
+    "sbo_mask_export_dev": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64]),
+    "sbo_pairs_set_global_unsafe_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
     "sbo_pairs_finish_dev": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.POINTER(PairResult), C.POINTER(C.c_int32)]),
     "sbo_kernel_launches": (C.c_int64, [_P, C.c_int]),
     "sbo_phase_ms": (C.c_int, [_P, C.c_int, _D]),

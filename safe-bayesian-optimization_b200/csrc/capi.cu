@@ -92,7 +92,7 @@ int sbo_destroy(sbo_ctx* ctx) {
                     &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->tile_bb, &ctx->nll_K, &ctx->nll_in, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
                     &ctx->m_tgt, &ctx->partials, &ctx->result, &ctx->scan_a, &ctx->scan_b, &ctx->xs_idx, &ctx->zs_idx,
                     &ctx->xs_pay, &ctx->zs_pay, &ctx->hits, &ctx->counts, &ctx->pairctr, &ctx->imp_rows, &ctx->vx, &ctx->vz,
-                    &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v, &ctx->key_x, &ctx->key_z, &ctx->perm_x, &ctx->perm_z, &ctx->sort_ws, &ctx->tile_keys, &ctx->item_mask, &ctx->item_list})
+                    &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v, &ctx->key_x, &ctx->key_z, &ctx->perm_x, &ctx->perm_z, &ctx->sort_ws, &ctx->tile_keys, &ctx->item_mask, &ctx->item_list, &ctx->gz_mask, &ctx->gz_idx, &ctx->gz_pay})
     free_buf(*b);
   ev_collect(ctx);
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -352,6 +352,25 @@ int sbo_pairs_export_dev(sbo_ctx* ctx, void* rows_dev, void* vrows_dev) {
 int sbo_pairs_import_dev(sbo_ctx* ctx, int64_t n_total, const void* rows_dev, const void* vrows_dev) {
   ENTER();
   return pairs_import(ctx, n_total, rows_dev, vrows_dev);
+}
+int sbo_pairs_set_segments(sbo_ctx* ctx, int nranks, int rank, const int64_t* n_per_rank) {
+  ENTER();
+  return pairs_set_segments(ctx, nranks, rank, n_per_rank);
+}
+int sbo_pairs_set_global_unsafe_dev(sbo_ctx* ctx, const void* gathered_words_dev, int64_t words_per_rank, int nranks) {
+  ENTER();
+  return pairs_set_global_unsafe(ctx, gathered_words_dev, words_per_rank, nranks);
+}
+int sbo_mask_export_dev(sbo_ctx* ctx, int mask_kind, int which, void* dst_dev, int64_t dst_words) {
+  ENTER();
+  SBO_REQUIRE(ctx->have_sets && dst_dev, "sbo_mask_export_dev: no sets");
+  const uint32_t* p = mask_ptr(ctx, mask_kind, which);
+  SBO_REQUIRE(p != nullptr, "mask not available");
+  const long long nw = mask_words(ctx);
+  SBO_REQUIRE(dst_words >= nw, "destination too small");
+  SBO_CUDA(cudaMemcpyAsync(dst_dev, p, sizeof(uint32_t) * (size_t)nw, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (dst_words > nw) SBO_CUDA(cudaMemsetAsync((uint32_t*)dst_dev + nw, 0, sizeof(uint32_t) * (size_t)(dst_words - nw), ctx->stream));
+  return SBO_OK;
 }
 int sbo_pairs_run_dev(sbo_ctx* ctx, int goose, void* result_dev) {
   ENTER();

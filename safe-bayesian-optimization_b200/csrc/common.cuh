@@ -113,6 +113,12 @@ struct PairStage {
   double beta = 0.0;
   double L[SBO_MAX_G] = {0, 0, 0, 0, 0, 0, 0, 0};   // L[c] for constraint c+1
   long long nx_local = 0, nz_local = 0, nz_full = 0, nx_total = 0, pairs_evaluated = 0;   // nz_local <= nz_full when pruned
+  // sharded runs: candidates per rank (prefix sums), this rank; canon: payloads re-ordered to grid order at import;
+  // nz_global >= 0: the Lipschitz expander pairs this rank's candidate tiles with ALL unsafe points (gz_* buffers)
+  int seg_n = 1, seg_rank = 0;
+  long long seg_off[65] = {0};
+  bool canon = false;
+  long long nz_global = -1;
 };
 
 struct sbo_ctx {
@@ -150,6 +156,7 @@ struct sbo_ctx {
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
   DevBuf key_x, key_z, perm_x, perm_z, sort_ws, tile_keys, item_mask, item_list;   // exact pruning of the fantasy expander
+  DevBuf gz_mask, gz_idx, gz_pay;         // all-gathered unsafe set of a sharded Lipschitz expander
   PairStage ps;
   // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
   struct EvPair { cudaEvent_t a, b; int phase; };
@@ -220,6 +227,8 @@ int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const doub
 int pairs_export(sbo_ctx* ctx, void* rows_dev, void* vrows_dev);
 int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const void* vrows_dev);
 int pairs_run(sbo_ctx* ctx, int goose, void* result_dev);
+int pairs_set_segments(sbo_ctx* ctx, int nranks, int rank, const int64_t* n_per_rank);
+int pairs_set_global_unsafe(sbo_ctx* ctx, const void* gathered_words_dev, long long words_per_rank, int nranks);
 int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_dev, sbo_pair_result* out, int32_t* counts_host);
 int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host);
 uint32_t* mask_ptr(sbo_ctx* ctx, int mask_kind, int which);

@@ -101,9 +101,10 @@ __global__ void __launch_bounds__(PT)
 k_pairs_expander(PairConsts pc, long long nx, long long nz, const double* __restrict__ xc, const double* __restrict__ ucb,
                  const double* __restrict__ thr, const double* __restrict__ zc, unsigned char* __restrict__ hits,
                  unsigned long long* __restrict__ pair_counter, long long z_per_split, const double* __restrict__ bb,
-                 long long ntiles) {
+                 long long ntiles, int tile_stride, int tile_offset, const int* __restrict__ out_pos) {
   __shared__ double zs[D][PT];
-  const long long t = (long long)blockIdx.x * PT + threadIdx.x;
+  // candidate tiles are dealt round-robin to the ranks of a sharded run (tile_stride = nranks, tile_offset = rank)
+  const long long t = ((long long)blockIdx.x * tile_stride + tile_offset) * PT + threadIdx.x;
   const bool active = t < nx;
   double x[D], u[SBO_MAX_G - 1], r2[SBO_MAX_G - 1];
   const unsigned full = (1u << pc.nc) - 1u;
@@ -153,8 +154,9 @@ k_pairs_expander(PairConsts pc, long long nx, long long nz, const double* __rest
     }
   }
   if (active) {
+    const long long o = out_pos ? out_pos[t] : t;      // hit flags go back in the caller's (gathered) candidate order
     for (int c = 0; c < pc.nc; ++c)
-      if ((found >> c) & 1u) hits[(size_t)c * nx + t] = 1;
+      if ((found >> c) & 1u) hits[(size_t)c * nx + o] = 1;
   }
   if (threadIdx.x == 0 && pair_counter) atomicAdd(pair_counter, tiles * (unsigned long long)PT * PT * pc.nc);
 }
@@ -234,9 +236,11 @@ k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restri
 template <int D>
 static int launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long long nx, long long nz, const double* xc,
                         const double* ucb, const double* thr, const double* zc, unsigned char* hits,
-                        unsigned long long* ctr) {
+                        unsigned long long* ctr, int tile_stride, int tile_offset, const int* out_pos) {
   const long long nthr = goose ? nz : nx, ntile = goose ? nx : nz;
-  const long long bx = cdiv(nthr, PT);
+  long long bx = cdiv(nthr, PT);
+  if (!goose && tile_stride > 1) bx = bx > tile_offset ? cdiv(bx - tile_offset, tile_stride) : 0;   // this rank's candidate tiles
+  if (bx == 0) return SBO_OK;
   long long splits = 1;
   const long long tiles = cdiv(ntile, PT);
   while (bx * splits < 4 * 148 && splits * 8 <= tiles && splits < 65535) splits *= 2;   // enough CTAs, >= 8 tiles each
@@ -253,7 +257,8 @@ static int launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long lon
   if (goose)
     k_pairs_target<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles);
   else
-    k_pairs_expander<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles);
+    k_pairs_expander<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles,
+                                                      tile_stride > 1 ? tile_stride : 1, tile_stride > 1 ? tile_offset : 0, out_pos);
   return SBO_OK;
 }
 
@@ -270,7 +275,49 @@ k_gather_coords(GridSpec gs, const long long* __restrict__ idx, long long n, dou
   for (int k = 0; k < gs.d; ++k) coords[(size_t)k * n + t] = x[k];
 }
 
-// export row of one local candidate (doubles): [coords[d] | ucb[nc] | xn[d] | a[nc] | b[nc]]
+// raw coordinates of points given by GLOBAL grid index (the all-gathered unsafe set of a sharded Lipschitz expander)
+__global__ void __launch_bounds__(256)
+k_gather_coords_global(GridSpec gs, const long long* __restrict__ gidx, long long n, double* __restrict__ coords) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double x[SBO_MAX_D];
+  point_coords(gs, gidx[t], x);
+  for (int k = 0; k < gs.d; ++k) coords[(size_t)k * n + t] = x[k];
+}
+// global bitmask over the whole grid from the ranks' local masks (rotated block-cyclic shards, common.cuh shard_global):
+// global word w lies in block b = w*32/blk, super-block sb = b/n, slot = b%n, owner r = (slot - rot(sb)) mod n,
+// where it is local word sb*(blk/32) + w%(blk/32) of that rank's mask.
+__global__ void __launch_bounds__(256)
+k_assemble_global_mask(long long n_words, long long blk, int nranks, const uint32_t* __restrict__ gathered,
+                       long long words_per_rank, uint32_t* __restrict__ out) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  const long long wpb = blk / 32, b = w / wpb, sb = b / nranks, n = nranks;
+  const long long slot = b % n, rot = (sb + sb / n + sb / (n * n)) % n;
+  const long long r = (slot - rot + n) % n;
+  const long long lw = sb * wpb + w % wpb;
+  out[w] = (lw < words_per_rank) ? gathered[(size_t)r * words_per_rank + lw] : 0u;
+}
+// canonical (ascending global index) slot of every gathered candidate row; the rows of each rank's segment are already
+// ascending, so the slot is a sum of lower bounds over the segments (deterministic on every rank)
+__global__ void __launch_bounds__(256)
+k_canon_perm(long long n, int nseg, const long long* __restrict__ seg_off, const double* __restrict__ rows, int RS,
+             int* __restrict__ perm) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double g = rows[(size_t)i * RS + RS - 1];
+  long long pos = 0;
+  for (int r = 0; r < nseg; ++r) {
+    long long lo = seg_off[r], hi = seg_off[r + 1];
+    if (i >= lo && i < hi) { pos += i - lo; continue; }
+    const long long base = lo;
+    while (lo < hi) { const long long m = (lo + hi) >> 1; if (rows[(size_t)m * RS + RS - 1] < g) lo = m + 1; else hi = m; }
+    pos += lo - base;
+  }
+  perm[pos] = (int)i;
+}
+
+// export row of one local candidate (doubles): [coords[d] | ucb[nc] | xn[d] | a[nc] | b[nc] | global grid index]
 //   a = beta*sigma/(sigma^2+sn2), b = 1/(sigma^2+sn2) in normalised units (fantasy update gains)
 __global__ void __launch_bounds__(256)
 k_export_rows(GridSpec gs, ModelSpec ms, double beta, const long long* __restrict__ idx, long long n,
@@ -278,11 +325,12 @@ k_export_rows(GridSpec gs, ModelSpec ms, double beta, const long long* __restric
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int d = gs.d, nc = ms.G - 1;
-  const int RS = 2 * d + 3 * nc;
+  const int RS = 2 * d + 3 * nc + 1;
   const long long p = idx[t];
   double x[SBO_MAX_D];
   point_coords(gs, shard_global(gs, p), x);
   double* r = rows + (size_t)t * RS;
+  r[RS - 1] = (double)shard_global(gs, p);             // exact below 2^53
   for (int k = 0; k < d; ++k) { r[k] = x[k]; r[d + nc + k] = (x[k] - ms.Xmean[k]) / ms.Xstd[k]; }
   for (int c = 0; c < nc; ++c) {
     const double m = mean[(size_t)(c + 1) * gs.count + p], v = var[(size_t)(c + 1) * gs.count + p];
@@ -316,7 +364,7 @@ k_import_rows(int d, int nc, long long n, PairConsts pc, const int* __restrict__
               double* __restrict__ bx) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const int RS = 2 * d + 3 * nc;
+  const int RS = 2 * d + 3 * nc + 1;
   const double* r = rows + (size_t)(perm ? perm[t] : t) * RS;        // slot t holds gathered candidate perm[t]
   for (int k = 0; k < d; ++k) { coords[(size_t)k * n + t] = r[k]; xn[(size_t)k * n + t] = r[d + nc + k]; }
   for (int c = 0; c < nc; ++c) {
@@ -424,7 +472,7 @@ __global__ void __launch_bounds__(256)
 k_key_x(int d, int nc, long long n, FantasyConsts fc, const double* __restrict__ rows, double* __restrict__ key) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const double* r = rows + (size_t)t * (2 * d + 3 * nc);
+  const double* r = rows + (size_t)t * (2 * d + 3 * nc + 1);
   double k = -INFINITY;
   for (int c = 0; c < nc; ++c) {
     const double kap = fmin(fmax(1.0 - fc.sn2[c] * r[2 * d + 2 * nc + c], 0.0), 1.0);
@@ -675,7 +723,7 @@ int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const doub
   PairStage& ps = ctx->ps;
   ps = PairStage{};
   ps.mode = mode; ps.precision = precision; ps.beta = beta;
-  ps.row_doubles = 2 * d + 3 * nc;
+  ps.row_doubles = 2 * d + 3 * nc + 1;
   if (mode == SBO_MODE_LIPSCHITZ) {
     SBO_REQUIRE(L != nullptr || nc == 0, "Lipschitz constants required");
     for (int c = 0; c < nc; ++c) ps.L[c] = L[c + 1];
@@ -801,6 +849,18 @@ int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const vo
     k_permute_key<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(n_total, (const int*)ctx->perm_x.p, kx + n_total, kx);
     SBO_LAUNCH_CHECK();
     xperm = (const int*)ctx->perm_x.p;
+  } else if (ps.seg_n > 1 && n_total > 0) {
+    // sharded Lipschitz run: restore grid order (spatially compact tiles for the bounding-box culling); the gathered rows
+    // are rank-major and each rank's cyclic blocks are scattered over the grid
+    SBO_REQUIRE(ps.seg_off[ps.seg_n] == n_total, "sbo_pairs_set_segments: the per-rank counts do not add up to n_total");
+    SBO_TRY(sbo_ensure(ctx, ctx->perm_x, sizeof(int) * (size_t)n_total));
+    SBO_TRY(sbo_ensure(ctx, ctx->sort_ws, sizeof(long long) * 64 + sizeof(int) * 2 * 4096 + 16));
+    SBO_CUDA(cudaMemcpyAsync(ctx->sort_ws.p, ps.seg_off, sizeof(long long) * (ps.seg_n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    k_canon_perm<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(n_total, ps.seg_n, (const long long*)ctx->sort_ws.p,
+                                                                          (const double*)rows_dev, ps.row_doubles, (int*)ctx->perm_x.p);
+    SBO_LAUNCH_CHECK();
+    xperm = (const int*)ctx->perm_x.p;
+    ps.canon = true;
   }
   k_import_rows<<<(unsigned)cdiv(n_total, 256), 256, 0, ctx->stream>>>(d, nc, n_total, pc, xperm, (const double*)rows_dev, xc, ucb, thr, xn, ax, bx);
   SBO_LAUNCH_CHECK();
@@ -816,6 +876,49 @@ int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const vo
     SBO_LAUNCH_CHECK();
   }
   ev_end(ctx);
+  return SBO_OK;
+}
+
+int pairs_set_segments(sbo_ctx* ctx, int nranks, int rank, const int64_t* n_per_rank) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared, "sbo_pairs_set_segments: call sbo_pairs_prepare first");
+  SBO_REQUIRE(nranks >= 1 && nranks <= 64 && rank >= 0 && rank < nranks && n_per_rank, "bad segments");
+  ps.seg_n = nranks; ps.seg_rank = rank;
+  ps.seg_off[0] = 0;
+  for (int r = 0; r < nranks; ++r) {
+    SBO_REQUIRE(n_per_rank[r] >= 0, "negative candidate count");
+    ps.seg_off[r + 1] = ps.seg_off[r] + n_per_rank[r];
+  }
+  return SBO_OK;
+}
+
+// gathered_words_dev: the ranks' LOCAL unsafe masks, words_per_rank words each (zero padded), rank-major
+int pairs_set_global_unsafe(sbo_ctx* ctx, const void* gathered_words_dev, long long words_per_rank, int nranks) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared && ps.mode == SBO_MODE_LIPSCHITZ, "sbo_pairs_set_global_unsafe_dev: prepare the Lipschitz pair stage first");
+  const GridSpec& gs = ctx->gs;
+  SBO_REQUIRE(nranks >= 1 && gathered_words_dev && words_per_rank >= 1, "bad gathered mask");
+  SBO_REQUIRE(nranks == 1 || (gs.cyc_n == nranks && gs.cyc_blk % 32 == 0), "the grid must be sharded with sbo_set_shard_cyclic over the same ranks");
+  const long long nwg = cdiv(gs.N, 32);
+  SBO_TRY(sbo_ensure(ctx, ctx->gz_mask, sizeof(uint32_t) * (size_t)nwg));
+  ev_begin(ctx, 6);
+  if (nranks == 1) {
+    SBO_CUDA(cudaMemcpyAsync(ctx->gz_mask.p, gathered_words_dev, sizeof(uint32_t) * (size_t)(nwg < words_per_rank ? nwg : words_per_rank),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    k_assemble_global_mask<<<(unsigned)cdiv(nwg, 256), 256, 0, ctx->stream>>>(nwg, gs.cyc_blk, nranks, (const uint32_t*)gathered_words_dev,
+                                                                               words_per_rank, (uint32_t*)ctx->gz_mask.p);
+    SBO_LAUNCH_CHECK();
+  }
+  long long nzg = 0;
+  SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->gz_mask.p, gs.N, ctx->gz_idx, &nzg));
+  if (nzg > 0) {
+    SBO_TRY(sbo_ensure(ctx, ctx->gz_pay, sizeof(double) * (size_t)nzg * gs.d));
+    k_gather_coords_global<<<(unsigned)cdiv(nzg, 256), 256, 0, ctx->stream>>>(gs, (const long long*)ctx->gz_idx.p, nzg, (double*)ctx->gz_pay.p);
+    SBO_LAUNCH_CHECK();
+  }
+  ev_end(ctx);
+  ps.nz_global = nzg;
   return SBO_OK;
 }
 
@@ -835,7 +938,7 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     SBO_REQUIRE(result_dev != nullptr, "null result buffer");
     SBO_CUDA(cudaMemsetAsync(result_dev, 0, res_bytes, ctx->stream));
   }
-  if (nx == 0 || nz == 0) return SBO_OK;
+  if (nx == 0 || (nz == 0 && !(ps.nz_global > 0 && !goose))) return SBO_OK;
   SBO_TRY(sbo_ensure(ctx, ctx->pairctr, 2 * sizeof(unsigned long long)));
   SBO_CUDA(cudaMemsetAsync(ctx->pairctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   unsigned long long* ctr = (unsigned long long*)ctx->pairctr.p;
@@ -845,19 +948,22 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     PairConsts pc{};
     pc.nc = nc; pc.beta = ps.beta;
     for (int c = 0; c < nc; ++c) pc.L[c] = ps.L[c];
-    const double* zc = (const double*)ctx->zs_pay.p;
+    // sharded SafeOpt expander: ALL unsafe points in grid order (sbo_pairs_set_global_unsafe_dev), this rank's share
+    // of the candidate tiles; GoOSE target and single-GPU runs: the local unsafe points, every candidate
+    const bool by_cand = !goose && ps.nz_global >= 0;
+    const double* zc = (const double*)(by_cand ? ctx->gz_pay.p : ctx->zs_pay.p);
+    const long long nzr = by_cand ? ps.nz_global : nz;
+    const int stride = by_cand ? ps.seg_n : 1, off = by_cand ? ps.seg_rank : 0;
+    const int* out_pos = (!goose && ps.canon) ? (const int*)ctx->perm_x.p : nullptr;
     unsigned char* hits = (unsigned char*)result_dev;
+    if (nzr == 0) return SBO_OK;
     ev_begin(ctx, 4);
+#define LP(DD) SBO_TRY(launch_pairs<DD>(ctx, goose, pc, nx, nzr, xc, ucb, thr, zc, hits, ctr, stride, off, out_pos))
     switch (d) {
-      case 1: SBO_TRY(launch_pairs<1>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      case 2: SBO_TRY(launch_pairs<2>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      case 3: SBO_TRY(launch_pairs<3>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      case 4: SBO_TRY(launch_pairs<4>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      case 5: SBO_TRY(launch_pairs<5>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      case 6: SBO_TRY(launch_pairs<6>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      case 7: SBO_TRY(launch_pairs<7>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
-      default: SBO_TRY(launch_pairs<8>(ctx, goose, pc, nx, nz, xc, ucb, thr, zc, hits, ctr)); break;
+      case 1: LP(1); break; case 2: LP(2); break; case 3: LP(3); break; case 4: LP(4); break;
+      case 5: LP(5); break; case 6: LP(6); break; case 7: LP(7); break; default: LP(8); break;
     }
+#undef LP
     SBO_LAUNCH_CHECK();
     ev_end(ctx);
     ps.counted = true;
@@ -925,7 +1031,7 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
   }
   unsigned long long h[2] = {0, 0};
   const long long nloc = goose ? nz : nx;
-  const bool have = nc > 0 && nloc > 0 && nxt > 0 && nz > 0 && result_dev != nullptr;
+  const bool have = nc > 0 && nloc > 0 && nxt > 0 && (nz > 0 || (!goose && ps.nz_global > 0)) && result_dev != nullptr;
   if (have) {
     ev_begin(ctx, 6);
     const long long* idx = (const long long*)(goose ? ctx->zs_idx.p : ctx->xs_idx.p);

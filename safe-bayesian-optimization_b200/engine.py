@@ -296,6 +296,17 @@ class GridEngine:
     def pairs_import(self, n_total, rows, vrows=None):
         self._ck(self._lib.sbo_pairs_import_dev(self._h, int(n_total), self._ptr(rows), self._ptr(vrows)))
 
+    def pairs_set_segments(self, n_per_rank, rank):
+        n = np.ascontiguousarray(np.asarray(n_per_rank, dtype=np.int64))
+        self._ck(self._lib.sbo_pairs_set_segments(self._h, int(n.size), int(rank), n.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def mask_export(self, kind, dst, which=0):
+        """Copy a local bitmask into a caller-owned device buffer of int32/uint32 words (zero padded)."""
+        self._ck(self._lib.sbo_mask_export_dev(self._h, int(kind), int(which), self._ptr(dst), int(dst.numel())))
+
+    def pairs_set_global_unsafe(self, gathered, words_per_rank, nranks):
+        self._ck(self._lib.sbo_pairs_set_global_unsafe_dev(self._h, self._ptr(gathered), int(words_per_rank), int(nranks)))
+
     def pairs_run(self, goose, result):
         self._ck(self._lib.sbo_pairs_run_dev(self._h, int(bool(goose)), self._ptr(result)))
 

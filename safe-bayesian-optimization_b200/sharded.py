@@ -152,6 +152,21 @@ def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
     nx, nz = int(info["n_x_local"]), int(info["n_z_local"])
     n_all = gather_scalars([nx], device, group)[:, 0].astype(np.int64)
     n_total, offset = int(n_all.sum()), int(n_all[:rank].sum())
+    fantasy = mode == capi.MODE_FANTASY
+    if not fantasy and world > 1 and hasattr(eng, "pairs_set_segments"):
+        # reference-exact mode: the library restores grid order of the gathered candidates (compact tiles for the exact
+        # culling), and the SafeOpt expander is split by CANDIDATES: all-gather of the unsafe bitmask (north_star's
+        # collective; N/8 bytes in total), every rank pairs its share of the candidate tiles with ALL unsafe points
+        eng.pairs_set_segments(n_all, rank)
+        if not goose:
+            wpr = int(gather_scalars([(eng.count + 31) // 32], device, group)[:, 0].max())
+            loc = torch.zeros(wpr, dtype=torch.int32, device=device)
+            eng.mask_export(capi.MASK_UNSAFE, loc)
+            allw = torch.empty(world * wpr, dtype=torch.int32, device=device)
+            _order(eng, device)
+            dist.all_gather_into_tensor(allw, loc, group=group)
+            _order(eng, device)
+            eng.pairs_set_global_unsafe(allw, wpr, world)
     tr.mark("prepare")
     vrow = int(info["vrow_bytes"])
     big = vrow * n_total > BIG_V_BYTES
@@ -178,7 +193,6 @@ def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
             torch.cuda.empty_cache()         # hand the gathered copy back before the GEMM workspaces are sized
     tr.mark("import")
     nc = eng.G - 1
-    fantasy = mode == capi.MODE_FANTASY
     if goose:
         result = torch.zeros(max(nc * nz, 1), dtype=torch.uint8, device=device)
     elif fantasy:

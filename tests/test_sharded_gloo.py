@@ -33,6 +33,36 @@ class OracleEngine:
         self.points = self.points_all[self.gidx]
         self.device = 0
         self.count = self.gidx.size
+        self.block, self.N = block, N
+        self.seg, self.gz = None, None
+
+    @staticmethod
+    def shard_gidx(rank, world, N, block):
+        nblk = (N + block - 1) // block
+        sb = np.arange((nblk + world - 1) // world)
+        mine = sb * world + (rank + sb + sb // world + sb // (world * world)) % world
+        mine = mine[mine < nblk]
+        return np.concatenate([np.arange(b * block, min(N, (b + 1) * block)) for b in mine])
+
+    # ---- sharded Lipschitz expander: segments, mask export, all-gathered unsafe set (sbo_pairs_set_segments,
+    # sbo_mask_export_dev, sbo_pairs_set_global_unsafe_dev)
+    def pairs_set_segments(self, n_per_rank, rank):
+        self.seg = (np.asarray(n_per_rank, dtype=np.int64), int(rank))
+
+    def mask_export(self, kind, dst, which=0):
+        assert kind == 2                                        # MASK_UNSAFE
+        bits = np.zeros(dst.numel() * 32, dtype=np.uint8)
+        bits[: self.count] = self.Z
+        dst.copy_(torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int32).copy()))
+
+    def pairs_set_global_unsafe(self, gathered, words_per_rank, nranks):
+        w = gathered.numpy().view(np.uint32).reshape(nranks, words_per_rank)
+        Zg = np.zeros(self.N, dtype=bool)
+        for r in range(nranks):
+            g = self.shard_gidx(r, nranks, self.N, self.block)
+            bits = np.unpackbits(w[r].view(np.uint8), bitorder="little")[: g.size].astype(bool)
+            Zg[g] = bits
+        self.gz = np.flatnonzero(Zg)
 
     def set_model(self, ds):
         self.ds = ds
@@ -76,15 +106,17 @@ class OracleEngine:
         self.mode, self.L = mode, (None if L is None else np.asarray(L))
         self.xs, self.zs = np.flatnonzero(self.S), np.flatnonzero(self.Z)
         nc, n = self.G - 1, self.ds["X_norm"].shape[0]
-        return {"n_x_local": self.xs.size, "n_z_local": self.zs.size, "row_doubles": 2 * self.d + 3 * nc,
+        self.seg, self.gz = None, None
+        return {"n_x_local": self.xs.size, "n_z_local": self.zs.size, "row_doubles": 2 * self.d + 3 * nc + 1,
                 "vrow_bytes": nc * n * 8 if mode == 1 else 0}
 
     def pairs_export(self, rows, vrows):
         O, ds, d, nc = self.O, self.ds, self.d, self.G - 1
         x = self.points[self.xs]
         xn = (x - ds["X_mean"]) / ds["X_std"]
-        r = np.zeros((self.xs.size, 2 * d + 3 * nc))
+        r = np.zeros((self.xs.size, 2 * d + 3 * nc + 1))
         r[:, :d] = x
+        r[:, -1] = self.gidx[self.xs]
         r[:, d + nc:2 * d + nc] = xn
         for c in range(nc):
             _, _, sn2 = O.unpack_hyper(ds["hypopt"][:, c + 1], d)
@@ -109,10 +141,23 @@ class OracleEngine:
         O, ds, d, nc = self.O, self.ds, self.d, self.G - 1
         z = self.points[self.zs]
         res = result.numpy()
-        if self.n_total == 0 or self.zs.size == 0 or nc == 0:
+        by_cand = self.mode == 0 and not goose and self.gz is not None
+        if self.n_total == 0 or nc == 0 or (self.zs.size == 0 and not by_cand):
             return
         x = self.rows[:, :d]
-        if self.mode == 0:
+        if by_cand:
+            # this rank's share of the candidate tiles (grid order, 256 per tile, dealt round-robin) x ALL unsafe points
+            world, rank = self.seg[0].size, self.seg[1]
+            order = np.argsort(self.rows[:, -1], kind="stable")
+            mine = np.concatenate([order[t:t + 256] for t in range(rank * 256, self.n_total, world * 256)] or [np.zeros(0, int)])
+            zg = self.points_all[self.gz]
+            if mine.size and zg.shape[0]:
+                diff = x[mine][:, None, :] - zg[None, :, :] + O.PAIR_OFFSET
+                dist_ = np.sqrt(np.sum(diff * diff, axis=2))
+                for c in range(nc):
+                    reach = (self.rows[mine, d + c][:, None] - self.L[c + 1] * dist_) >= 0.0
+                    res[c * self.n_total + mine] = reach.any(axis=1)
+        elif self.mode == 0:
             diff = x[:, None, :] - z[None, :, :] + O.PAIR_OFFSET
             dist_ = np.sqrt(np.sum(diff * diff, axis=2))
             for c in range(nc):
