@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "tf32x3"),
                     help="fantasy GEMM operands: tf32x3 (default: split TF32, FP32-class accuracy, meets the 1e-4 tolerance), tf32 (single pass), fp64")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end repetitions (default max(2, steps); the first is dropped when > 1)")
+    ap.add_argument("--orchestrator", default="library", choices=["library", "torch"],
+                    help="multi-GPU: collectives inside libsbo_b200 (sbo_comm_init, default) or issued by sharded.py through torch.distributed")
+    ap.add_argument("--c5", type=int, default=-1, help="1: add the C5 north-star step (2^24-point d=6 grid, n=2048) as an extra key; "
+                    "default: on at --gpus 8 (the configuration BASELINE.json states the target on), off otherwise")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--no-lipschitz-steps", action="store_true", help="skip the reference-exact SafeOpt/GoOSE step times (extra key)")
@@ -270,6 +274,92 @@ def measure_peaks(torch, dev):
     return out
 
 
+def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
+    """BASELINE.json configs[4] / the north-star target: one warm-up + one timed SafeOpt fantasy step on the 2^24-point
+    d=6 grid with n=2048 observations, grid-sharded over the ranks.  Single-pass TF32 with the exact pruning: the
+    split-TF32 operands (2 x 41 GB of gathered candidate rows) do not fit next to the z side at this size."""
+    from sbo_b200 import workloads, sharded
+    ds5, lo5, hi5, pts5, beta5 = workloads.c5()
+    n5, d5 = ds5["X_norm"].shape
+    out = {"workload": "C5: synthetic step, d=6, N=16^6=2^24 grid, n=2048, G=4 (3 constraints)", "precision": "tf32", "n_gpus": world}
+    try:
+        eng.release(3)
+        torch.cuda.empty_cache()
+        eng.set_grid(lo5, hi5, pts5)
+        if world > 1:
+            eng.set_shard_cyclic(rank, world, 256)
+        free0, total = torch.cuda.mem_get_info(dev)
+        # every rank must have the head-room (the step peaks at ~135 GB per GPU on 8): agree BEFORE any collective of the
+        # step is entered, so that a rank that cannot run it does not leave the others waiting
+        need = (135 << 30) * 8 // max(world, 8) if world >= 8 else (1 << 62)
+        ok = torch.tensor([1 if free0 >= need else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            out["skipped"] = f"needs {need >> 30} GB free per GPU on >= 8 GPUs (free here: {free0 >> 30} GB, {world} ranks)"
+            return out
+
+        def step5():
+            with torch.cuda.stream(stream):
+                if world == 1:
+                    return eng.safeopt_step(ds5, beta5, mode="fantasy", precision="tf32")
+                return sharded.safeopt_step(eng, ds5, beta5, mode="fantasy", precision="tf32")
+        step5()
+        torch.cuda.synchronize()
+        free_min = torch.cuda.mem_get_info(dev)[0]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            r5 = step5()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        ph = eng.phase_ms()
+        ex5 = r5["expander"]
+        pairs5, ev5 = int(ex5["pairs_algorithmic"]), int(ex5["pairs_evaluated"])
+        flops = ev5 / world * (2.0 * n5 + 3 * d5 + 20)
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = mp.get("bf16_tflops_sustained", 1387.2) / 2.0
+        ach = flops / (ph["pairs"] * 1e-3) / 1e12 if ph["pairs"] > 0 else None
+        out.update({"ms_per_step": ms, "value": pairs5 / (ms * 1e-3), "unit": "pair-evals/s", "pairs": pairs5, "pairs_evaluated": ev5,
+                    "n_safe": int(r5["n_safe"]), "n_unsafe": int(r5["n_unsafe"]), "n_min": int(r5["n_min"]), "n_hit": int(ex5["n_hit"]),
+                    "x_new_idx": int(r5["x_new_idx"]), "phase_ms_rank0": ph,
+                    "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
+                                 "kernel": "tc::k_fantasy_tc2 (tf32), per GPU, evaluated pairs only"},
+                    "device_mem_high_water_gb": (total - min(free_min, torch.cuda.mem_get_info(dev)[0])) / 2 ** 30,
+                    "device_mem_total_gb": total / 2 ** 30, "steps": 1, "warmup": 1})
+        # parity at full size: this rank's posterior on a random sample of its shard against the FP64 oracle
+        if rank == 0:
+            from oracle import gp_oracle as O
+            m, v = eng.posterior(keep_v=0)
+            rng = np.random.default_rng(0)
+            cnt = eng.count
+            sel = np.sort(rng.choice(cnt, size=128, replace=False))
+            sb = sel // 256
+            gidx = ((sb * world + (rank + sb + sb // world + sb // (world * world)) % world) * 256 + sel % 256) if world > 1 else sel
+            axes = O.grid_axes(lo5, hi5, pts5)
+            P = np.column_stack([axes[k][(gidx // (pts5[0] ** k)) % pts5[0]] for k in range(d5)])
+            mo, vo = O.posterior_chol(P, ds5)
+            em = max(np.max(np.abs(m[sel, i] - mo[:, i])) / max(np.max(np.abs(mo[:, i])), ds5["Y_std"][i]) for i in range(4))
+            ev = max(np.max(np.abs(v[sel, i] - vo[:, i])) / (O.unpack_hyper(ds5["hypopt"][:, i], d5)[1] * ds5["Y_std"][i] ** 2) for i in range(4))
+            out["posterior_parity_rank0_sample"] = {"points": 128, "mean_rel_err": float(em), "var_rel_err": float(ev), "tol": 1e-10,
+                                                    "ok": bool(em <= 1e-10 and ev <= 1e-10)}
+        eng.release(3)
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        out["error"] = repr(e)[:400]
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -294,6 +384,10 @@ def run_ours(args):
     eng.set_grid(lo, hi, pts)
     if world > 1:
         eng.set_shard_cyclic(rank, world, 256)      # block-cyclic ownership balances |S| and |Z| over the ranks
+        if args.orchestrator == "library":          # the library's own NCCL communicator: collectives inside the C ABI
+            from sbo_b200 import sharded as _shc
+            with torch.cuda.stream(stream):
+                _shc.init_comm(eng, dev)
     fantasy = args.mode == "fantasy"
     eng.set_option("fantasy_prune", int(args.prune))
 
@@ -380,6 +474,12 @@ def run_ours(args):
                                                     "x_new_idx": int(rl["x_new_idx"])}
         lip["note"] = ("end-to-end wall time (host buffers) of one acquisition step with the reference's Lipschitz pair test "
                        "(SafeOpt.py:85-124, GoOSE.py:80-119), exact tile culling on; max over ranks")
+    c5 = None
+    if (args.c5 == 1 or (args.c5 < 0 and world == 8)) and args.workload == "c4":
+        c5 = c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier)
+        eng.set_grid(lo, hi, pts)
+        if world > 1:
+            eng.set_shard_cyclic(rank, world, 256)
     pairs = int(ex["pairs_algorithmic"])            # sharded.safeopt_step already returns the global count
     if rank != 0:
         if world > 1:
@@ -443,6 +543,18 @@ def run_ours(args):
             "roofline": roof, "peaks": {**peaks, "hbm_gbs": mp.get("hbm_gbs"), "bf16_tflops": mp.get("bf16_tflops")}}
     if lip is not None:
         line["lipschitz_mode"] = lip
+    if c5 is not None:
+        if c5.get("pairs") and not args.no_cpu_baseline:       # the CPU arm on the same box, same model (bounded sample)
+            from oracle import cpu_arm
+            from sbo_b200 import workloads as _wl
+            ds5, lo5, hi5, pts5, beta5 = _wl.c5()
+            cores5 = use_all_host_threads()
+            s5 = cpu_arm.sample_step(ds5, lo5, hi5, pts5, beta5, "fantasy", seed=0, n_points=8192, n_x=1024, n_z=16384)
+            t5 = cpu_arm.extrapolate(s5, int(np.prod(pts5)), c5["pairs"])
+            c5["cpu_baseline"] = {"value": c5["pairs"] / t5, "unit": "pair-evals/s", "cores": cores5, "kind": "port",
+                                  "seconds_per_step_extrapolated": t5, "sample": cpu_arm.describe(s5, int(np.prod(pts5)), c5["pairs"], "fantasy")}
+            c5["speedup_vs_cpu_port"] = t5 / (c5["ms_per_step"] * 1e-3)
+        line["c5"] = c5
     if world == 1 and not args.no_reference_configs:
         line["reference_configs"] = reference_configs(eng, torch)
     if not args.no_cpu_baseline and world == 1:

@@ -194,6 +194,30 @@ int sbo_pairs_set_global_unsafe_dev(sbo_ctx* ctx, const void* gathered_words_dev
 #define SBO_MASK_EXPANDER 4
 #define SBO_MASK_TARGET   5
 
+/* ---- multi-GPU: library-owned communicator and whole sharded steps -------------------
+ * One process per GPU, one context per process, the grid sharded with sbo_set_shard_cyclic(rank, nranks, block).
+ * NCCL is resolved at run time (dlopen libnccl.so.2): no torch / framework needed on the host side.
+ *   sbo_comm_unique_id  rank 0 creates the 128-byte ncclUniqueId and distributes it to the other ranks by any host
+ *                       mechanism (file, MPI, socket, torch.distributed ...)
+ *   sbo_comm_init       collective: every rank joins the communicator
+ * sbo_safeopt_step_sharded / sbo_goose_step_sharded run  posterior -> sets -> (Lipschitz constants) -> pair stage ->
+ * arg-reductions -> x_new  with the collectives issued on the context's stream between the kernels; every rank gets
+ * the same GLOBAL result.  The model must have been installed on every rank (sbo_set_model).  Decision rules:
+ * test/test_SafeOpt.py:144-158, test/test_GoOSE.py:151-162.  L = NULL: Lipschitz constants from the grid
+ * (SafeOpt.py:68-83), constraint G-1's for every constraint like the reference (SafeOpt.py:110). */
+typedef struct sbo_step_result {
+  sbo_sets_result sets;            /* global sets: sizes, min_S ucb_0 / lcb_0, minimiser (SafeOpt) */
+  double L[SBO_MAX_G];             /* global Lipschitz constants (Lipschitz mode, when computed) */
+  sbo_pair_result pairs;           /* expander (SafeOpt) or target (GoOSE): global optima and totals */
+  int64_t x_new_idx, explore_idx;  /* chosen next query point (global grid index); GoOSE: nearest safe point or -1 */
+} sbo_step_result;
+int sbo_comm_unique_id(void* id128);
+int sbo_comm_init(sbo_ctx* ctx, int rank, int nranks, const void* id128);
+int sbo_comm_destroy(sbo_ctx* ctx);
+int sbo_safeopt_step_sharded(sbo_ctx* ctx, double beta, int mode, int precision, int unsafe_rule, const double* L /* G or NULL */,
+                             sbo_step_result* out);
+int sbo_goose_step_sharded(sbo_ctx* ctx, double beta, int unsafe_rule, const double* L /* G or NULL */, sbo_step_result* out);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this library launched on ctx since the last reset */
 int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
@@ -202,6 +226,7 @@ int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
 /* tuning / diagnosis options (defaults reproduce the documented behaviour; none changes a result):
  *   "posterior_variant"  1 (default) FP64 tensor cores (DMMA) | 0 FP64 SIMT register tiles
+ *   "posterior_chunk_mb" size of the cross-covariance tile one posterior chunk keeps between its two kernels (default 48: L2 resident)
  *   "fantasy_variant"    -1 (default) auto | bit 0: 256-column z tiles, bit 1: 8 epilogue warps, bit 2: 2-CTA pairs
  *   "fantasy_gx"         x tile pairs per raster group of the 2-CTA GEMM (0 = default: a quarter of the clusters)
  *   "fantasy_prune"      1 (default): exact pruning of the fantasy expander -- candidates and unsafe points are ordered by the

@@ -38,6 +38,11 @@ class PairResult(C.Structure):
                 ("pairs_algorithmic", C.c_int64), ("pairs_evaluated", C.c_int64), ("n_hit", C.c_int64)]
 
 
+class StepResult(C.Structure):
+    _fields_ = [("sets", SetsResult), ("L", C.c_double * MAX_G), ("pairs", PairResult),
+                ("x_new_idx", C.c_int64), ("explore_idx", C.c_int64)]
+
+
 class PairsInfo(C.Structure):
     _fields_ = [("n_x_local", C.c_int64), ("n_z_local", C.c_int64), ("row_doubles", C.c_int64), ("vrow_bytes", C.c_int64)]
 
@@ -83,6 +88,11 @@ SIGNATURES = {
     "sbo_mask_export_dev": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64]),
     "sbo_pairs_set_global_unsafe_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
     "sbo_pairs_finish_dev": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.POINTER(PairResult), C.POINTER(C.c_int32)]),
+    "sbo_comm_unique_id": (C.c_int, [_P]),
+    "sbo_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "sbo_comm_destroy": (C.c_int, [_P]),
+    "sbo_safeopt_step_sharded": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.c_int, _D, C.POINTER(StepResult)]),
+    "sbo_goose_step_sharded": (C.c_int, [_P, C.c_double, C.c_int, _D, C.POINTER(StepResult)]),
     "sbo_kernel_launches": (C.c_int64, [_P, C.c_int]),
     "sbo_phase_ms": (C.c_int, [_P, C.c_int, _D]),
     "sbo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),

@@ -87,6 +87,7 @@ int sbo_create(int device, sbo_ctx** out) {
 int sbo_destroy(sbo_ctx* ctx) {
   if (!ctx) return SBO_OK;
   cudaSetDevice(ctx->device);
+  sbo_comm_destroy(ctx);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->Xn, &ctx->Yn, &ctx->alpha, &ctx->W, &ctx->Kmat, &ctx->info, &ctx->pts, &ctx->mean, &ctx->var,
                     &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->tile_bb, &ctx->nll_K, &ctx->nll_in, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
@@ -417,6 +418,7 @@ int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value) {
   ENTER();
   SBO_REQUIRE(name != nullptr, "null option name");
   if (!strcmp(name, "posterior_variant")) { ctx->opt_posterior_variant = value; return SBO_OK; }
+  if (!strcmp(name, "posterior_chunk_mb")) { ctx->opt_posterior_chunk_mb = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_variant")) { ctx->opt_fantasy_variant = value; return SBO_OK; }
   if (!strcmp(name, "pair_cull")) { ctx->opt_pair_cull = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_gx")) { ctx->opt_fantasy_gx = value; return SBO_OK; }

@@ -121,8 +121,11 @@ struct PairStage {
   long long nz_global = -1;
 };
 
+struct sbo_comm;   // comm.cu: NCCL communicator + gathered buffers
+
 struct sbo_ctx {
   int device = 0;
+  sbo_comm* comm = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   std::string err;
@@ -169,6 +172,7 @@ struct sbo_ctx {
   long long n_unsafe_local = 0;
   int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps;
                                      // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
+  int64_t opt_posterior_chunk_mb = 0; // Kx scratch per chunk in MB (0 = default 48: L2 resident)
   int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles
   int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };

@@ -405,10 +405,18 @@ static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, i
   return SBO_OK;
 }
 
-// points per chunk so that the Kx scratch stays below ~1 GiB
-static long long chunk_points(const ModelSpec& ms, long long count) {
+// Points per chunk.  The cross-covariance tile Kx[G][npad][P] is produced by k_crosscov and consumed by the solve kernel
+// of the same chunk; sized to stay resident in the 126 MB L2 (option "posterior_chunk_mb", default 48 MB) it never
+// makes the round trip through HBM that a 1 GiB scratch did (ncu r01: 16 GB written + 17 GB read at C4).  Never fewer
+// points than one full wave of the solve kernel needs (2 CTAs of 64 points per SM and GP).
+static long long chunk_points(const sbo_ctx* ctx, const ModelSpec& ms, long long count) {
   const size_t per_pt = (size_t)ms.G * ms.npad * sizeof(double);
-  long long p = (long long)((size_t)1 << 30) / (long long)per_pt;
+  const long long mb = ctx->opt_posterior_chunk_mb > 0 ? ctx->opt_posterior_chunk_mb : 48;
+  long long p = (long long)((size_t)mb << 20) / (long long)per_pt;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const long long wave = (long long)cdiv((long long)sms * 2, ms.G) * 64;     // points that fill one wave of the solve kernel
+  if (p < wave) p = wave;
   p = (p / 128) * 128;
   if (p < 128) p = 128;
   const long long need = cdiv(count, 128) * 128;
@@ -426,7 +434,7 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   SBO_TRY(sbo_ensure(ctx, ctx->mean, sizeof(double) * (size_t)ms.G * count));
   SBO_TRY(sbo_ensure(ctx, ctx->var, sizeof(double) * (size_t)ms.G * count));
   SBO_TRY(sbo_ensure(ctx, ctx->lmax, sizeof(double) * SBO_MAX_G));
-  const long long P = chunk_points(ms, count);
+  const long long P = chunk_points(ctx, ms, count);
   SBO_TRY(sbo_ensure(ctx, ctx->kx, sizeof(double) * (size_t)ms.G * ms.npad * P));
   ctx->keep_v = 0;
   if (keep_v && ms.G > 1) {
@@ -473,7 +481,7 @@ int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, dou
   const ModelSpec& ms = ctx->ms;
   SBO_TRY(sbo_ensure(ctx, mbuf, sizeof(double) * (size_t)ms.G * m));
   SBO_TRY(sbo_ensure(ctx, vbuf, sizeof(double) * (size_t)ms.G * m));
-  const long long P = chunk_points(ms, m);
+  const long long P = chunk_points(ctx, ms, m);
   SBO_TRY(sbo_ensure(ctx, kbuf, sizeof(double) * (size_t)ms.G * ms.npad * P));
   for (long long p0 = 0; p0 < m; p0 += P) {
     const int valid = (int)((m - p0) < P ? (m - p0) : P);
@@ -499,7 +507,7 @@ int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, doubl
   SBO_TRY(points_common(ctx, m, x, tmp, xbuf));
   const ModelSpec& ms = ctx->ms;
   SBO_TRY(sbo_ensure(ctx, gbuf, sizeof(double) * (size_t)ms.d * m));
-  const long long P = chunk_points(ms, m);
+  const long long P = chunk_points(ctx, ms, m);
   SBO_TRY(sbo_ensure(ctx, kbuf, sizeof(double) * (size_t)ms.G * ms.npad * P));
   for (long long p0 = 0; p0 < m; p0 += P) {
     const int valid = (int)((m - p0) < P ? (m - p0) : P);

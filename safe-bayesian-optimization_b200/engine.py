@@ -41,13 +41,14 @@ class GridEngine:
         self.first = 0
         self.count = 0
         self.grid_kind = None
+        self.comm_ready = False
         self.stream = None                  # the raw cudaStream_t the context launches on (None = its own stream)
         if stream is not None:
             self._ck(self._lib.sbo_set_stream(self._h, C.c_void_p(int(stream))))
             self.stream = int(stream)
         import os
         for env, opt in (("SBO_FANTASY_VARIANT", "fantasy_variant"), ("SBO_POSTERIOR_VARIANT", "posterior_variant"),
-                         ("SBO_FANTASY_GX", "fantasy_gx")):
+                         ("SBO_FANTASY_GX", "fantasy_gx"), ("SBO_POSTERIOR_CHUNK_MB", "posterior_chunk_mb")):
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
 
@@ -321,6 +322,52 @@ class GridEngine:
         if counts is not None:
             out["counts"] = counts
         return out
+
+    # -- library-owned communicator + whole sharded steps (csrc/comm.cu) ---------------------------------
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._ck(self._lib.sbo_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self._lib.sbo_comm_init(self._h, int(rank), int(nranks), C.cast(buf, C.c_void_p)))
+        self.comm_ready = True
+
+    def _step_dict(self, r, goose):
+        out = self._sets_dict(r.sets)
+        out["L"] = np.array([r.L[i] for i in range(self.G)])
+        pr = self._pair_dict(r.pairs)
+        out["x_new_idx"], out["explore_idx"] = r.x_new_idx, r.explore_idx
+        if goose:
+            out["target"] = pr
+            out["target_idx"], out["target_lcb"] = pr["best_idx"], pr["best_value"]
+        else:
+            out["expander"] = pr
+            out["expander_idx"] = pr["best_idx"]
+            out["expander_std"] = float(np.sqrt(pr["best_value"])) if pr["best_idx"] >= 0 else 0.0
+            out["minimizer_std"] = float(np.sqrt(out["minimizer_var"])) if out["minimizer_idx"] >= 0 else 0.0
+        return out
+
+    def safeopt_step_sharded(self, ds, beta, mode="lipschitz", precision="fp64", unsafe_rule=capi.UNSAFE_ALL, L=None, upload=True):
+        """One SafeOpt step on a grid sharded over the ranks of the library's communicator (sbo_comm_init); the
+        collectives run inside the library.  Every rank returns the same global result."""
+        if upload:
+            self.set_model(ds)
+        prec, _ = capi.PRECISIONS[precision]
+        r = capi.StepResult()
+        Lp = capi.dptr(_f64(L)) if L is not None else None
+        self._ck(self._lib.sbo_safeopt_step_sharded(self._h, float(beta), capi.MODE_FANTASY if mode == "fantasy" else capi.MODE_LIPSCHITZ,
+                                                    int(prec), int(unsafe_rule), Lp, C.byref(r)))
+        return self._step_dict(r, False)
+
+    def goose_step_sharded(self, ds, beta, unsafe_rule=capi.UNSAFE_ALL, L=None, upload=True):
+        if upload:
+            self.set_model(ds)
+        r = capi.StepResult()
+        Lp = capi.dptr(_f64(L)) if L is not None else None
+        self._ck(self._lib.sbo_goose_step_sharded(self._h, float(beta), int(unsafe_rule), Lp, C.byref(r)))
+        return self._step_dict(r, True)
 
     # -- whole steps (drivers' decision rules) ------------------------------------------------
     def safeopt_step(self, ds, beta, mode="lipschitz", precision="fp64", unsafe_rule=capi.UNSAFE_ALL, L=None,

@@ -23,6 +23,21 @@ from . import _capi as capi
 
 
 # ---------------------------------------------------------------------------------------------
+# library-owned communicator (csrc/comm.cu): torch.distributed only carries the 128-byte NCCL id to the ranks
+# ---------------------------------------------------------------------------------------------
+def init_comm(eng, device=None, group=None):
+    """Create the library's own NCCL communicator over the ranks of `group`; afterwards safeopt_step / goose_step run
+    with every collective inside the library (sbo_safeopt_step_sharded / sbo_goose_step_sharded)."""
+    device = torch.device("cuda", eng.device) if device is None else device
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(eng.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    eng.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+
+# ---------------------------------------------------------------------------------------------
 # small collectives
 # ---------------------------------------------------------------------------------------------
 def _sync(device):
@@ -229,6 +244,8 @@ def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
 def safeopt_step(eng, ds, beta, mode="lipschitz", precision="fp64", unsafe_rule=capi.UNSAFE_ALL, L=None, upload=True,
                  device=None, group=None):
     """test/test_SafeOpt.py:144-158 on a sharded grid.  Every rank returns the same global result."""
+    if getattr(eng, "comm_ready", False) and group is None:
+        return eng.safeopt_step_sharded(ds, beta, mode=mode, precision=precision, unsafe_rule=unsafe_rule, L=L, upload=upload)
     device = torch.device("cuda", eng.device) if device is None else device
     fantasy = mode == "fantasy"
     prec, kv = capi.PRECISIONS[precision]
@@ -250,6 +267,8 @@ def safeopt_step(eng, ds, beta, mode="lipschitz", precision="fp64", unsafe_rule=
 
 def goose_step(eng, ds, beta, unsafe_rule=capi.UNSAFE_ALL, L=None, upload=True, device=None, group=None, coords=None):
     """test/test_GoOSE.py:151-162 on a sharded grid."""
+    if getattr(eng, "comm_ready", False) and group is None:
+        return eng.goose_step_sharded(ds, beta, unsafe_rule=unsafe_rule, L=L, upload=upload)
     device = torch.device("cuda", eng.device) if device is None else device
     out = _posterior_and_sets(eng, ds, beta, unsafe_rule, with_grad=L is None, keep_v=0, upload=upload, device=device,
                               group=group, need_pass2=False)

@@ -17,16 +17,27 @@ def _run(cmd):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("mode,precision", [("fantasy", "tf32"), ("lipschitz", "fp64")])
-def test_two_gpus_agree_with_one(mode, precision):
+@pytest.mark.parametrize("mode,precision,orchestrator", [
+    ("fantasy", "tf32x3", "library"), ("fantasy", "tf32", "torch"), ("lipschitz", "fp64", "library"), ("lipschitz", "fp64", "torch")])
+def test_two_gpus_agree_with_one(mode, precision, orchestrator):
+    """orchestrator = library: sbo_comm_init + sbo_*_step_sharded (collectives inside the C ABI, csrc/comm.cu);
+    torch: sharded.py issues them through torch.distributed.  Both must reproduce the single-GPU step, including the
+    reference-exact SafeOpt/GoOSE steps bench.py reports under `lipschitz_mode` (candidate-sharded expander)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     common = ["--workload", "c4s", "--mode", mode, "--precision", precision, "--steps", "1", "--warmup", "1",
-              "--no-cpu-baseline", "--no-peaks"]
+              "--no-cpu-baseline", "--no-peaks", "--no-reference-configs"]
     one = _run([sys.executable, "bench.py"] + common)
     two = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                "--master-addr", "127.0.0.1", "--master-port", "29533", "bench.py", "--gpus", "2"] + common)
+                "--master-addr", "127.0.0.1", "--master-port", "29533", "bench.py", "--gpus", "2",
+                "--orchestrator", orchestrator] + common)
     for k in ["n_safe", "n_unsafe", "n_min", "pairs", "n_hit", "x_new_idx"]:
         assert one["config"][k] == two["config"][k], k
     assert two["n_gpus"] == 2
+    for kind in ("safeopt", "goose"):
+        a, b = one["lipschitz_mode"][kind], two["lipschitz_mode"][kind]
+        for k in ("pairs", "n_hit", "x_new_idx"):
+            assert a[k] == b[k], (kind, k)
+        if kind == "safeopt":        # split by candidates: the early exit and the culling do the single-GPU work, shared
+            assert b["pairs_evaluated"] <= 1.1 * a["pairs_evaluated"] + 4 * 256 * 256 * 3
