@@ -79,6 +79,11 @@ int sbo_set_model(sbo_ctx* ctx, int n, int d, int G,
                   const double* X_mean, const double* X_std,
                   const double* Y_mean, const double* Y_std,
                   const double* hyp);
+/* One more observation at FIXED hyper-parameters and FIXED normalisation: x_norm_new[d],
+ * y_norm_new[G] in the normalised units of the installed model.  Rank-1 update of the factor on the device -- new row of
+ * L, of W = L^-1 and a refreshed alpha, O(n^2) -- instead of the rebuild + O(n^3) inverse of GP.add_sample
+ * (models/GP_Safe.py:283-304, which also re-fits and re-normalises; use sbo_set_model for that semantics). */
+int sbo_append_sample(sbo_ctx* ctx, const double* x_norm_new, const double* y_norm_new);
 /* debug / test read-back (any pointer may be NULL): K,L,W are [G][n][n] row-major, alpha [G][n] */
 int sbo_get_model(sbo_ctx* ctx, double* L, double* W, double* alpha);
 
@@ -136,6 +141,15 @@ int sbo_posterior_dev(sbo_ctx* ctx, void** mean_dev, void** var_dev);
 /* ---- arg-reductions (deterministic, lowest-index tie-break): SafeOpt.py:65,112; GoOSE.py:65,102,118 */
 int sbo_argreduce(sbo_ctx* ctx, int reduce_kind, int mask_kind, int which, const double* target /* d or NULL */,
                   int64_t* idx, double* value);
+
+/* ---- StableOpt on the grid (models/StableOpt.py:96-160): the meshgrid's first n_controlled axes are x_c, the others
+ * the disturbance d.  Robust safe set {x_c : min_d lcb_i(x_c,d) >= 0 for all constraints} (Minimise_d, :147-149),
+ * score(x_c) = max_d fun_0(x_c,d) with fun = 0 mean | 1 ucb | 2 lcb (Maximise_d, :151), and the arg-min of the score over
+ * the robust safe set (Minimize_Maximise, :153).  xc_idx indexes the x_c sub-grid (x_0 fastest), -1 = empty set;
+ * score (optional, host) receives max_d fun_0 for every x_c.  Needs sbo_posterior on the whole, unsharded meshgrid;
+ * option "prior_mean_zero" = 1 installs the zero prior mean of GP_Robust.py:322-323 at the next sbo_set_model. */
+int sbo_stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value,
+                      int64_t* n_robust_safe, double* score);
 
 /* ---- expander / target pair kernels ----------------------------------------------------------
  * Lipschitz mode (reference-exact): pair test  ucb_idx(x) - L_idx*||x - z + 1e-8||_2 >= 0 with
@@ -232,6 +246,7 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
  *   "fantasy_prune"      1 (default): exact pruning of the fantasy expander -- candidates and unsafe points are ordered by the
  *                        Cauchy-Schwarz keys of csrc/pairs.cu (k_key_x / k_key_z) and only tile pairs whose keys can meet
  *                        are evaluated; FP64 counts are unchanged | 0: every pair goes through the GEMM
+ *   "prior_mean_zero"    1: zero prior mean for every GP at the next sbo_set_model (GP_Robust.py, StableOpt) | 0 (default) GP_Safe.py:331
  *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
 /* ---- hyper-parameter fit:  GP.negative_loglikelihood  (GP_Safe.py:169-192), batched ------

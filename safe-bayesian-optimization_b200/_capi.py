@@ -61,6 +61,8 @@ SIGNATURES = {
     "sbo_version": (C.c_int, []),
     "sbo_set_model": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, _D, _D, _D, _D, _D, _D]),
     "sbo_get_model": (C.c_int, [_P, _D, _D, _D]),
+    "sbo_append_sample": (C.c_int, [_P, _D, _D]),
+    "sbo_stable_minmax": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _I64, _D, _I64, _D]),
     "sbo_set_grid": (C.c_int, [_P, C.c_int, _I64, _D, _D]),
     "sbo_set_points": (C.c_int, [_P, C.c_int64, C.c_int, _D]),
     "sbo_set_shard": (C.c_int, [_P, C.c_int64, C.c_int64]),

@@ -93,7 +93,7 @@ int sbo_destroy(sbo_ctx* ctx) {
                     &ctx->kx, &ctx->lmax, &ctx->vall, &ctx->tile_bb, &ctx->nll_K, &ctx->nll_in, &ctx->m_safe, &ctx->m_unsafe, &ctx->m_min, &ctx->m_user, &ctx->m_exp,
                     &ctx->m_tgt, &ctx->partials, &ctx->result, &ctx->scan_a, &ctx->scan_b, &ctx->xs_idx, &ctx->zs_idx,
                     &ctx->xs_pay, &ctx->zs_pay, &ctx->hits, &ctx->counts, &ctx->pairctr, &ctx->imp_rows, &ctx->vx, &ctx->vz,
-                    &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v, &ctx->key_x, &ctx->key_z, &ctx->perm_x, &ctx->perm_z, &ctx->sort_ws, &ctx->tile_keys, &ctx->item_mask, &ctx->item_list, &ctx->gz_mask, &ctx->gz_idx, &ctx->gz_pay})
+                    &ctx->aux_x, &ctx->aux_z, &ctx->pp_x, &ctx->pp_m, &ctx->pp_v, &ctx->pp_k, &ctx->pp_g, &ctx->tc_row, &ctx->tc_col, &ctx->tc_err, &ctx->exp_rows, &ctx->exp_v, &ctx->key_x, &ctx->key_z, &ctx->perm_x, &ctx->perm_z, &ctx->sort_ws, &ctx->tile_keys, &ctx->item_mask, &ctx->item_list, &ctx->gz_mask, &ctx->gz_idx, &ctx->gz_pay, &ctx->st_score, &ctx->st_mask})
     free_buf(*b);
   ev_collect(ctx);
   for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -403,6 +403,17 @@ int sbo_nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double
   return nll_batch(ctx, n, d, X_norm, y, P, hyp, nll);
 }
 
+int sbo_append_sample(sbo_ctx* ctx, const double* x_norm_new, const double* y_norm_new) {
+  ENTER();
+  return model_append(ctx, x_norm_new, y_norm_new);
+}
+
+int sbo_stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value,
+                      int64_t* n_robust_safe, double* score) {
+  ENTER();
+  return stable_minmax(ctx, n_controlled, fun_kind, beta, xc_idx, value, n_robust_safe, score);
+}
+
 int sbo_release(sbo_ctx* ctx, int what) {
   ENTER();
   SBO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -420,6 +431,7 @@ int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "posterior_variant")) { ctx->opt_posterior_variant = value; return SBO_OK; }
   if (!strcmp(name, "posterior_chunk_mb")) { ctx->opt_posterior_chunk_mb = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_variant")) { ctx->opt_fantasy_variant = value; return SBO_OK; }
+  if (!strcmp(name, "prior_mean_zero")) { ctx->opt_prior_mean_zero = value; return SBO_OK; }
   if (!strcmp(name, "pair_cull")) { ctx->opt_pair_cull = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_gx")) { ctx->opt_fantasy_gx = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_prune")) { ctx->opt_fantasy_prune = value; return SBO_OK; }

@@ -159,6 +159,7 @@ struct sbo_ctx {
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
   DevBuf key_x, key_z, perm_x, perm_z, sort_ws, tile_keys, item_mask, item_list;   // exact pruning of the fantasy expander
+  DevBuf st_score, st_mask;               // StableOpt: per-x_c worst-case score and robust-safe bitmask
   DevBuf gz_mask, gz_idx, gz_pay;         // all-gathered unsafe set of a sharded Lipschitz expander
   PairStage ps;
   // timing: event pairs are recorded without host syncs and summed per phase by ev_collect()
@@ -173,6 +174,7 @@ struct sbo_ctx {
   int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps;
                                      // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
   int64_t opt_posterior_chunk_mb = 0; // Kx scratch per chunk in MB (0 = default 48: L2 resident)
+  int64_t opt_prior_mean_zero = 0;    // 1: zero prior mean for every GP (GP_Robust.py:322-323, StableOpt); 0: GP_Safe.py:331-332
   int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles
   int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };
@@ -218,6 +220,8 @@ static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b;
 int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const double* Y_norm,
                  const double* X_mean, const double* X_std, const double* Y_mean, const double* Y_std,
                  const double* hyp);
+int model_append(sbo_ctx* ctx, const double* x_norm_new, const double* y_norm_new);
+int stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value, int64_t* n_robust_safe, double* score_host);
 int nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll);
 int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v);
 int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, double* var);

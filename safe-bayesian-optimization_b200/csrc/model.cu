@@ -187,7 +187,8 @@ int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const 
   for (int k = 0; k < d; ++k) { ms.Xmean[k] = X_mean[k]; ms.Xstd[k] = X_std[k]; }
   for (int g = 0; g < G; ++g) {
     ms.Ymean[g] = Y_mean[g]; ms.Ystd[g] = Y_std[g];
-    ms.m0[g] = (g == 0) ? 0.0 : (-2.0 * Y_mean[g]) / Y_std[g];                 // GP_Safe.py:331-332
+    // GP_Safe.py:331-332; option prior_mean_zero: the zero prior of GP_Robust.py:322-323 (StableOpt's model)
+    ms.m0[g] = (g == 0 || ctx->opt_prior_mean_zero) ? 0.0 : (-2.0 * Y_mean[g]) / Y_std[g];
     for (int k = 0; k < d; ++k) ms.inv_ell[g][k] = 1.0 / exp(2.0 * hyp[(size_t)k * G + g]);   // :338
     ms.sf2[g] = exp(2.0 * hyp[(size_t)d * G + g]);
     ms.sn2[g] = exp(2.0 * hyp[(size_t)(d + 1) * G + g]) + SBO_EPS_F32;         // :229
@@ -248,6 +249,125 @@ int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const 
   return SBO_OK;
 }
 
+
+// =============================================================================================
+// Rank-1 append: one new observation at FIXED hyper-parameters and FIXED normalisation.
+// The reference's add_sample (GP_Safe.py:283-304) re-fits and re-normalises, i.e. rebuilds K and inv(K) from scratch
+// (O(n^3)); at fixed hyper-parameters the factor only gains one row:
+//   l = L^-1 k_new = W k_new ,  l_nn = sqrt(k(x,x) + sn2 - |l|^2) ,  L' = [[L, 0], [l^T, l_nn]] ,
+//   W' = L'^-1 = [[W, 0], [-(l^T W)/l_nn, 1/l_nn]] ,  alpha' = W'^T W' (y' - m0)            -- O(n^2) per GP.
+// One CTA per GP; rows n of the padded L and W (identity rows until now) are overwritten in place.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_append_row(ModelSpec ms, int n_old, double* __restrict__ Lm, double* __restrict__ Wm,
+                                                    double* __restrict__ scratch, int* __restrict__ info) {
+  __shared__ double red[8];
+  __shared__ double s_lnn;
+  const int g = blockIdx.x, np = ms.npad, d = ms.d;
+  double* Lg = Lm + (size_t)g * np * np;
+  double* Wg = Wm + (size_t)g * np * np;
+  double* kv = scratch + (size_t)g * 2 * np;     // k_new[0..n_old)
+  double* lv = kv + np;                           // l[0..n_old)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* xnew = ms.Xn + (size_t)n_old * d;
+  for (int j = threadIdx.x; j < n_old; j += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) { const double df = ms.Xn[(size_t)j * d + k] - xnew[k]; s += df * df * ms.inv_ell[g][k]; }
+    kv[j] = ms.sf2[g] * exp(-0.5 * s);
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int r = warp; r < n_old; r += 8) {          // l_r = sum_{c<=r} W[r][c] k[c]   (one warp per row, coalesced)
+    double s = 0.0;
+    for (int c = lane; c <= r; c += 32) s += Wg[(size_t)r * np + c] * kv[c];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) { lv[r] = s; part += s * s; }
+  }
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double q = 0.0;
+    for (int w = 0; w < 8; ++w) q += red[w];
+    const double piv = ms.sf2[g] + ms.sn2[g] - q;
+    if (!(piv > 0.0)) { atomicExch(info + g, n_old + 1); s_lnn = 1.0; } else s_lnn = sqrt(piv);
+  }
+  __syncthreads();
+  const double lnn = s_lnn;
+  for (int c = threadIdx.x; c < n_old; c += blockDim.x) {     // new rows: L[n][c] = l_c, W[n][c] = -(sum_{r>=c} l_r W[r][c]) / l_nn
+    double s = 0.0;
+    for (int r = c; r < n_old; ++r) s += lv[r] * Wg[(size_t)r * np + c];
+    Lg[(size_t)n_old * np + c] = lv[c];
+    Wg[(size_t)n_old * np + c] = -s / lnn;
+  }
+  if (threadIdx.x == 0) { Lg[(size_t)n_old * np + n_old] = lnn; Wg[(size_t)n_old * np + n_old] = 1.0 / lnn; }
+}
+
+int model_append(sbo_ctx* ctx, const double* x_norm_new, const double* y_norm_new) {
+  SBO_REQUIRE(ctx->have_model, "sbo_append_sample: no model (call sbo_set_model)");
+  SBO_REQUIRE(x_norm_new && y_norm_new, "null pointer");
+  ModelSpec& ms = ctx->ms;
+  const int n = ms.n, d = ms.d, G = ms.G;
+  SBO_REQUIRE(n + 1 <= 16384, "n out of range");
+  ev_reset(ctx, 0);
+  ev_begin(ctx, 0);
+  if (n + 1 > ms.npad) {
+    // grow the padded factor by one 128-row block: copy L and W into wider matrices, identity on the new diagonal
+    const int np0 = ms.npad, np1 = np0 + 128;
+    DevBuf nK, nW, nX, nA;
+    SBO_TRY(sbo_ensure(ctx, nK, sizeof(double) * (size_t)G * np1 * np1));
+    SBO_TRY(sbo_ensure(ctx, nW, sizeof(double) * (size_t)G * np1 * np1));
+    SBO_TRY(sbo_ensure(ctx, nX, sizeof(double) * (size_t)np1 * d));
+    SBO_TRY(sbo_ensure(ctx, nA, sizeof(double) * (size_t)G * np1 * 2));
+    SBO_CUDA(cudaMemsetAsync(nK.p, 0, sizeof(double) * (size_t)G * np1 * np1, ctx->stream));
+    SBO_CUDA(cudaMemsetAsync(nW.p, 0, sizeof(double) * (size_t)G * np1 * np1, ctx->stream));
+    SBO_CUDA(cudaMemsetAsync(nX.p, 0, sizeof(double) * (size_t)np1 * d, ctx->stream));
+    SBO_CUDA(cudaMemcpyAsync(nX.p, ctx->Xn.p, sizeof(double) * (size_t)np0 * d, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<double> ones(128, 1.0);
+    for (int g = 0; g < G; ++g) {
+      for (DevBuf* pr : {&nK, &nW}) {
+        const double* src = (const double*)(pr == &nK ? ctx->Kmat.p : ctx->W.p) + (size_t)g * np0 * np0;
+        double* dst = (double*)pr->p + (size_t)g * np1 * np1;
+        SBO_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * np1, src, sizeof(double) * np0, sizeof(double) * np0, np0, cudaMemcpyDeviceToDevice, ctx->stream));
+        SBO_CUDA(cudaMemcpy2DAsync(dst + (size_t)np0 * np1 + np0, sizeof(double) * (np1 + 1), ones.data(), sizeof(double), sizeof(double), 128,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+      }
+    }
+    SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (DevBuf* b : {&ctx->Kmat, &ctx->W, &ctx->Xn, &ctx->alpha}) { cudaFree(b->p); }
+    ctx->Kmat = nK; ctx->W = nW; ctx->Xn = nX; ctx->alpha = nA;
+    ms.npad = np1;
+    ms.Xn = (const double*)ctx->Xn.p; ms.alpha = (const double*)ctx->alpha.p; ms.W = (const double*)ctx->W.p;
+  }
+  const int np = ms.npad;
+  // append the inputs (device copies of X_norm / Y_norm grow by one row)
+  DevBuf nY;
+  SBO_TRY(sbo_ensure(ctx, nY, sizeof(double) * (size_t)(n + 1) * G));
+  SBO_CUDA(cudaMemcpyAsync(nY.p, ctx->Yn.p, sizeof(double) * (size_t)n * G, cudaMemcpyDeviceToDevice, ctx->stream));
+  SBO_CUDA(cudaMemcpyAsync((double*)nY.p + (size_t)n * G, y_norm_new, sizeof(double) * G, cudaMemcpyHostToDevice, ctx->stream));
+  SBO_CUDA(cudaMemcpyAsync((double*)ctx->Xn.p + (size_t)n * d, x_norm_new, sizeof(double) * d, cudaMemcpyHostToDevice, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->Yn.p);
+  ctx->Yn = nY;
+  SBO_TRY(sbo_ensure(ctx, ctx->pp_k, sizeof(double) * (size_t)G * 2 * np));
+  SBO_CUDA(cudaMemsetAsync(ctx->info.p, 0, sizeof(int) * SBO_MAX_G, ctx->stream));
+  k_append_row<<<G, 256, 0, ctx->stream>>>(ms, n, (double*)ctx->Kmat.p, (double*)ctx->W.p, (double*)ctx->pp_k.p, (int*)ctx->info.p);
+  SBO_LAUNCH_CHECK();
+  ms.n = n + 1;
+  k_alpha<<<G, 256, 0, ctx->stream>>>(ms, (const double*)ctx->Yn.p, (double*)ctx->alpha.p + (size_t)G * np, (double*)ctx->alpha.p);
+  SBO_LAUNCH_CHECK();
+  int info[SBO_MAX_G];
+  SBO_CUDA(cudaMemcpyAsync(info, ctx->info.p, sizeof(int) * SBO_MAX_G, cudaMemcpyDeviceToHost, ctx->stream));
+  ev_end(ctx);
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  ev_collect(ctx);
+  for (int g = 0; g < G; ++g)
+    if (info[g] != 0) {
+      ctx->have_model = false;
+      return sbo_fail(ctx, SBO_ERR_NUMERIC, "appended sample makes K of GP " + std::to_string(g) + " numerically singular");
+    }
+  ctx->have_post = ctx->have_grad = ctx->have_sets = ctx->have_sets2 = false;
+  return SBO_OK;
+}
 
 // =============================================================================================
 // Batched negative log-likelihood for the hyper-parameter fit.

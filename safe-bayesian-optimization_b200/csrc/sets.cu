@@ -308,6 +308,50 @@ __global__ void __launch_bounds__(ST) k_argreduce_final(const RedPartial* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// StableOpt on the grid (models/StableOpt.py:96-160 of the reference).  The GP input is
+// (x_c, d): controlled axes first (fastest), disturbance axes last, so grid point p = q + Nxc*j with q the x_c index
+// and j the disturbance index.  One thread per x_c walks its disturbance column:
+//   robust safe  R = {q : min_j lcb_i(q,j) >= 0 for every constraint i}        (Minimise_d(lcb, xc, i) >= 0, :147-149)
+//   score(q)     = max_j fun_0(q,j),  fun = mean | ucb | lcb                   (Maximise_d(fun, xc, 0), :151)
+// and the outer DE of Minimize_Maximise (:153) becomes a masked arg-min of score over R (lowest index on ties).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST)
+k_stable_columns(int G, long long N, long long Nxc, long long Nd, const double* __restrict__ mean, const double* __restrict__ var,
+                 double beta, int fun_kind, double* __restrict__ score, uint32_t* __restrict__ robust_w, RedPartial* __restrict__ part) {
+  __shared__ ArgVal sm_av[ST / 32];
+  const long long q = (long long)blockIdx.x * ST + threadIdx.x;
+  bool safe = false;
+  ArgVal a{INFINITY, SBO_IDX_NONE};
+  if (q < Nxc) {
+    double worst[SBO_MAX_G];
+    for (int i = 1; i < G; ++i) worst[i] = INFINITY;
+    double best = -INFINITY;
+    for (long long j = 0; j < Nd; ++j) {
+      const long long p = q + Nxc * j;
+      const double m0 = mean[p], v0 = var[p];
+      const double f = fun_kind == 0 ? m0 : (fun_kind == 1 ? ucb_of(m0, v0, beta) : lcb_of(m0, v0, beta));
+      best = fmax(best, f);
+      for (int i = 1; i < G; ++i) worst[i] = fmin(worst[i], lcb_of(mean[(size_t)i * N + p], var[(size_t)i * N + p], beta));
+    }
+    safe = true;
+    for (int i = 1; i < G; ++i) safe = safe && (worst[i] >= 0.0);
+    score[q] = best;
+    if (safe) a = ArgVal{best, q};
+  }
+  const uint32_t w = __ballot_sync(0xffffffffu, safe);
+  if ((threadIdx.x & 31) == 0 && q < Nxc) robust_w[q >> 5] = w;
+  a = block_argmin(a, sm_av);
+  if (threadIdx.x == 0) part[blockIdx.x] = RedPartial{a.v, a.i};
+}
+__global__ void __launch_bounds__(256) k_popcount_words(const uint32_t* __restrict__ w, long long nw, unsigned long long* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned c = (i < nw) ? __popc(w[i]) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // stream compaction of a bitmask into ascending LOCAL indices
 // ---------------------------------------------------------------------------------------------
 #define SC_WORDS 1024   // words per scan block
@@ -537,5 +581,49 @@ int argreduce_run(sbo_ctx* ctx, int kind, const uint32_t* mask_dev, const double
   ev_collect(ctx);
   if (idx) *idx = r.i;
   if (value) *value = (kind == SBO_ARGMIN_DIST && r.i >= 0) ? sqrt(r.v) : r.v;
+  return SBO_OK;
+}
+
+// StableOpt: robust safe set + min-max over the disturbance axes of the meshgrid (see k_stable_columns)
+int stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value, int64_t* n_robust_safe,
+                  double* score_host) {
+  SBO_REQUIRE(ctx->have_post, "sbo_stable_minmax: no posterior (call sbo_posterior)");
+  const GridSpec& gs = ctx->gs;
+  SBO_REQUIRE(gs.kind == 1 && gs.cyc_n <= 1 && gs.first == 0 && gs.count == gs.N, "sbo_stable_minmax needs the whole meshgrid on this context");
+  SBO_REQUIRE(n_controlled >= 1 && n_controlled < gs.d, "controlled dimensions must be 1 .. d-1 (the rest are disturbances)");
+  SBO_REQUIRE(fun_kind >= 0 && fun_kind <= 2, "fun_kind: 0 mean, 1 ucb, 2 lcb");
+  long long Nxc = 1;
+  for (int k = 0; k < n_controlled; ++k) Nxc *= gs.pts[k];
+  const long long Nd = gs.N / Nxc;
+  const int nblocks = (int)cdiv(Nxc, ST);
+  SBO_TRY(sbo_ensure(ctx, ctx->st_score, sizeof(double) * (size_t)Nxc));
+  SBO_TRY(sbo_ensure(ctx, ctx->st_mask, sizeof(uint32_t) * (size_t)cdiv(Nxc, 32)));
+  SBO_TRY(sbo_ensure(ctx, ctx->partials, sizeof(SetsPartial) * (size_t)nblocks));
+  SBO_TRY(sbo_ensure(ctx, ctx->result, sizeof(SetsDeviceResult) + sizeof(RedPartial)));
+  RedPartial* part = (RedPartial*)ctx->partials.p;
+  RedPartial* res = (RedPartial*)((char*)ctx->result.p + sizeof(SetsDeviceResult));
+  SBO_TRY(sbo_ensure(ctx, ctx->pairctr, 2 * sizeof(unsigned long long)));
+  unsigned long long* cnt = (unsigned long long*)ctx->pairctr.p;
+  SBO_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+  ev_reset(ctx, 3);
+  ev_begin(ctx, 3);
+  k_stable_columns<<<nblocks, ST, 0, ctx->stream>>>(ctx->ms.G, gs.N, Nxc, Nd, (const double*)ctx->mean.p, (const double*)ctx->var.p, beta,
+                                                   fun_kind, (double*)ctx->st_score.p, (uint32_t*)ctx->st_mask.p, part);
+  SBO_LAUNCH_CHECK();
+  k_argreduce_final<<<1, ST, 0, ctx->stream>>>(part, nblocks, 0, res);
+  SBO_LAUNCH_CHECK();
+  k_popcount_words<<<(unsigned)cdiv(cdiv(Nxc, 32), 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->st_mask.p, cdiv(Nxc, 32), cnt);
+  SBO_LAUNCH_CHECK();
+  ev_end(ctx);
+  RedPartial r;
+  unsigned long long c = 0;
+  SBO_CUDA(cudaMemcpyAsync(&r, res, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  if (score_host) SBO_CUDA(cudaMemcpyAsync(score_host, ctx->st_score.p, sizeof(double) * (size_t)Nxc, cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  ev_collect(ctx);
+  if (xc_idx) *xc_idx = r.i;
+  if (value) *value = r.v;
+  if (n_robust_safe) *n_robust_safe = (int64_t)c;
   return SBO_OK;
 }

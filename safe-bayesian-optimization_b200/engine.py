@@ -102,6 +102,25 @@ class GridEngine:
                                          capi.dptr(ym), capi.dptr(ys), capi.dptr(hyp)))
         self.n, self.d, self.G = n, d, G
 
+    def append_sample(self, x_norm_new, y_norm_new):
+        """Rank-1 append at fixed hyper-parameters / normalisation (sbo_append_sample): n -> n + 1."""
+        x, y = _f64(x_norm_new).reshape(-1), _f64(y_norm_new).reshape(-1)
+        if x.shape[0] != self.d or y.shape[0] != self.G:
+            raise ValueError("x_norm_new must have d entries and y_norm_new G entries")
+        self._ck(self._lib.sbo_append_sample(self._h, capi.dptr(x), capi.dptr(y)))
+        self.n += 1
+
+    def stable_minmax(self, n_controlled, fun="ucb", beta=2.0, want_scores=False):
+        """StableOpt on the grid: (x_c index, min over the robust safe set of max_d fun_0, |robust safe set|[, scores])."""
+        kind = {"mean": 0, "ucb": 1, "lcb": 2}[fun]
+        idx, val, cnt = C.c_int64(), C.c_double(), C.c_int64()
+        sc, sp = None, None
+        if want_scores:
+            sc = np.empty(int(np.prod(self.grid_shape[:n_controlled])))
+            sp = capi.dptr(sc)
+        self._ck(self._lib.sbo_stable_minmax(self._h, int(n_controlled), kind, float(beta), C.byref(idx), C.byref(val), C.byref(cnt), sp))
+        return (idx.value, val.value, cnt.value, sc) if want_scores else (idx.value, val.value, cnt.value)
+
     def nll_batch(self, X_norm, y, hyp_pop):
         """GP.negative_loglikelihood (GP_Safe.py:169-192) for a population: hyp_pop (P, d+2) -> nll (P,)."""
         Xn, yv, hp = _f64(X_norm), _f64(y).reshape(-1), _f64(hyp_pop)

@@ -182,6 +182,26 @@ class GP:
             self.hypopt, self.invKopt = self.determine_hyperparameters(self.X_norm, self.Y_norm)
             self.update_inference_dataset()
 
+    def add_sample_fixed(self, x_new, y_new):
+        """Additive: one more observation at FIXED hyper-parameters and FIXED
+        normalisation constants -- what a controller does between two re-fits.  The device appends one row to the
+        Cholesky factor and refreshes W = L^-1 and alpha in O(n^2) (``sbo_append_sample``); nothing is re-uploaded and
+        the O(n^3) ``inv(K)`` of GP_Safe.py:232 is not formed (``invKopt`` is dropped from ``inference_datasets``:
+        the grid path never reads it).  ``add_sample`` keeps the reference's re-fit + re-normalise semantics."""
+        self._ensure_uploaded(self.inference_datasets)
+        x_new = np.asarray(x_new, dtype=np.float64).reshape(1, -1)
+        y_new = np.asarray(y_new, dtype=np.float64).reshape(1, -1)
+        xn, yn = (x_new - self.X_mean) / self.X_std, (y_new - self.Y_mean) / self.Y_std
+        self.engine.append_sample(xn, yn)
+        self.X, self.Y = np.vstack([self.X, x_new]), np.vstack([self.Y, y_new])
+        self.X_norm, self.Y_norm = np.vstack([self.X_norm, xn]), np.vstack([self.Y_norm, yn])
+        self.n_point = self.X.shape[0]
+        self.invKopt = None
+        self.update_inference_dataset()
+        ds = self.inference_datasets                    # the device already holds this state: no upload on the next call
+        self._uploaded = (id(ds), self._version, id(ds.get("hypopt")), id(ds.get("X_norm")))
+        self._on_model_changed()
+
     # ------------------------------------------------------------------ inference (GPU)
     def GP_inference(self, x, inference_dataset):
         """GP_Safe.py:310-352 on the B200: returns (mean (G,), var (G,)), or mean[0] if not var_out."""

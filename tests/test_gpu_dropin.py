@@ -256,3 +256,74 @@ def test_trust_region_minimize_obj_lcb(oracle, c1):
     centre, radius = bo.update_TR(x_old, x_min, r_old, y_old, bo.calculate_plant_outputs(x_min))
     assert radius in (pytest.approx(r_old * 0.8), pytest.approx(r_old), pytest.approx(min(r_old * 1.1, 1)))
     assert np.array_equal(centre, x_old) or np.array_equal(centre, x_min)
+
+
+def test_append_sample_matches_factorisation_from_scratch(engine, oracle):
+    """sbo_append_sample (rank-1 update at fixed hyper-parameters and normalisation) against
+    sbo_set_model of the grown data set: factor, W, alpha and the grid posterior; n crosses a 128-row padding boundary."""
+    from sbo_b200 import workloads
+    ds, lo, hi, pts, beta = workloads.small(d=3, pts_per_dim=10, n=132, seed=3, G=3)
+    n0 = 126
+    base = dict(ds)
+    base["X_norm"], base["Y_norm"] = ds["X_norm"][:n0], ds["Y_norm"][:n0]
+    engine.set_grid(lo, hi, pts)
+    engine.set_model(base)
+    for j in range(n0, 132):
+        engine.append_sample(ds["X_norm"][j], ds["Y_norm"][j])
+    La, Wa, aa = engine.get_model()
+    ma, va = engine.posterior()
+    engine.set_model(ds)
+    Lb, Wb, ab = engine.get_model()
+    mb, vb = engine.posterior()
+    assert np.max(np.abs(La - Lb)) <= 1e-11 * np.max(np.abs(Lb))
+    assert np.max(np.abs(Wa - Wb)) <= 1e-9 * np.max(np.abs(Wb))
+    assert np.max(np.abs(aa - ab)) <= 1e-8 * np.max(np.abs(ab))
+    assert np.max(np.abs(ma - mb)) <= 1e-9 * np.max(np.abs(mb))
+    assert np.max(np.abs(va - vb)) <= 1e-9 * np.max(ds["Y_std"]) ** 2
+
+
+def test_stableopt_minmax_on_the_grid(oracle):
+    """StableOpt's Minimize_Maximise / Maximise_d / Minimise_d (models/StableOpt.py:96-154) on the joint (x_c, d) grid
+    against the oracle posterior with the zero prior mean of GP_Robust.py:322-323."""
+    from sbo_b200 import workloads
+    from sbo_b200.models import StableOpt
+    ds, lo, hi, pts, beta = workloads.small(d=3, pts_per_dim=10, n=60, seed=5, G=3)
+    bo = StableOpt.BO([None] * 3, np.column_stack([lo[:2], hi[:2]]), np.column_stack([lo[2:], hi[2:]]), beta,
+                      grid_points_per_dim=[14, 13, 9])
+    bo.X_mean, bo.X_std, bo.Y_mean, bo.Y_std = ds["X_mean"], ds["X_std"], ds["Y_mean"], ds["Y_std"]
+    bo.X_norm, bo.Y_norm, bo.hypopt, bo.invKopt = ds["X_norm"], ds["Y_norm"], ds["hypopt"], None
+    bo.n_point, bo.nx_dim, bo.ny_dim, bo.var_out, bo.kernel = 60, 3, 3, True, "RBF"
+    bo.update_inference_dataset()
+    P = oracle.make_grid(lo, hi, [14, 13, 9])
+    zero = dict(ds)
+    orig = oracle.prior_mean
+    try:
+        oracle.prior_mean = lambda d_: np.zeros(d_["Y_norm"].shape[1])          # GP_Robust: zero prior mean
+        mean, var = oracle.posterior_chol(P, zero)
+    finally:
+        oracle.prior_mean = orig
+    lcb, ucb = oracle.bounds(mean, var, beta)
+    Nxc = 14 * 13
+    worst = lcb[:, 1:].reshape(9, Nxc, 2).min(axis=0)                           # min over d (slowest axis) per x_c
+    R = (worst >= 0.0).all(axis=1)
+    for name, arr in (("ucb", ucb[:, 0]), ("mean", mean[:, 0]), ("lcb", lcb[:, 0])):
+        score = arr.reshape(9, Nxc).max(axis=0)
+        x, val = bo.Minimize_Maximise(getattr(bo, name))
+        assert bo.n_robust_safe == R.sum()
+        if R.any():
+            io, vo = oracle.masked_argmin(score, R)
+            assert np.allclose(x, P[io, :2]) and val == pytest.approx(vo, rel=1e-9)
+        else:
+            assert np.isnan(x).all() and val == np.inf
+    xc = np.array([0.11, -0.23])
+    D = np.linspace(lo[2], hi[2], 9)
+    pts = np.column_stack([np.tile(xc, (9, 1)), D])
+    try:
+        oracle.prior_mean = lambda d_: np.zeros(d_["Y_norm"].shape[1])
+        mo, vo = oracle.posterior_chol(pts, zero)
+    finally:
+        oracle.prior_mean = orig
+    assert bo.Maximise_d(bo.ucb, xc, 1) == pytest.approx(np.max(mo[:, 1] + beta * np.sqrt(vo[:, 1])), rel=1e-9)
+    assert bo.Minimise_d(bo.lcb, xc, 2) == pytest.approx(np.min(mo[:, 2] - beta * np.sqrt(vo[:, 2])), rel=1e-9)
+    bo.engine.set_option("prior_mean_zero", 0)
+    bo.engine.close()
