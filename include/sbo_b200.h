@@ -240,7 +240,7 @@ int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
 /* tuning / diagnosis options (defaults reproduce the documented behaviour; none changes a result):
  *   "posterior_variant"  1 (default) FP64 tensor cores (DMMA) | 0 FP64 SIMT register tiles
- *   "posterior_chunk_mb" size of the cross-covariance tile one posterior chunk keeps between its two kernels (default 48: L2 resident)
+ *   "posterior_chunk_mb" size of the cross-covariance tile one posterior chunk keeps between its two kernels in MB (default 1024; 24-96 keeps it L2 resident but measured slower at C4)
  *   "fantasy_variant"    -1 (default) auto | bit 0: 256-column z tiles, bit 1: 8 epilogue warps, bit 2: 2-CTA pairs
  *   "fantasy_gx"         x tile pairs per raster group of the 2-CTA GEMM (0 = default: a quarter of the clusters)
  *   "fantasy_prune"      1 (default): exact pruning of the fantasy expander -- candidates and unsafe points are ordered by the

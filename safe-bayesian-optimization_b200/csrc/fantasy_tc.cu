@@ -320,10 +320,12 @@ k_fantasy_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_wait(bar_empty(stage), phase ^ 1, p.err, 1);
             mbar_expect_tx(bar_full(stage), C::STAGE_BYTES);
             const uint32_t sa = tiles + stage * C::STAGE_BYTES;
-            // split-TF32 rows are [hi | lo]: K segments (x_hi,z_hi), (x_hi,z_lo), (x_lo,z_hi)
-            const int seg = kb / p.nkb, kk = (kb - seg * p.nkb) * BK;
-            tma_load_3d(sa, &tmA, bar_full(stage), kk + (seg == 2 ? p.npad : 0), xt * BM, c);
-            tma_load_3d(sa + BM * 128, &tmB, bar_full(stage), kk + (seg == 1 ? p.npad : 0), zt * BN, c);
+            // split-TF32 rows are [hi | lo]: K segments (x_hi,z_lo), (x_lo,z_hi), then (x_hi,z_hi).  The two small
+            // cross terms are accumulated FIRST, while the FP32 accumulator is still ~2^-11 of its final size, so the
+            // tensor core's per-step accumulation rounding (one ulp of the running sum) cannot swallow them.
+            const int seg = p.split ? kb / p.nkb : 2, kk = (kb - (p.split ? seg : 0) * p.nkb) * BK;
+            tma_load_3d(sa, &tmA, bar_full(stage), kk + (seg == 1 ? p.npad : 0), xt * BM, c);
+            tma_load_3d(sa + BM * 128, &tmB, bar_full(stage), kk + (seg == 0 ? p.npad : 0), zt * BN, c);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
       }
@@ -620,9 +622,9 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (rank == 0) mbar_expect_tx(bar_full(stage), 2 * C::STAGE_BYTES);
             const uint32_t full_leader = mapa_u32(bar_full(stage), 0);
             const uint32_t sa = tiles + stage * C::STAGE_BYTES;
-            const int seg = kb / p.nkb, kk = (kb - seg * p.nkb) * BK;
-            tma_load_3d_2sm(sa, &tmA, full_leader, kk + (seg == 2 ? p.npad : 0), xt * 2 * BM + (int)rank * BM, c);
-            tma_load_3d_2sm(sa + BM * 128, &tmB, full_leader, kk + (seg == 1 ? p.npad : 0), zt * BN + (int)rank * (BN / 2), c);
+            const int seg = p.split ? kb / p.nkb : 2, kk = (kb - (p.split ? seg : 0) * p.nkb) * BK;   // cross terms first (see above)
+            tma_load_3d_2sm(sa, &tmA, full_leader, kk + (seg == 1 ? p.npad : 0), xt * 2 * BM + (int)rank * BM, c);
+            tma_load_3d_2sm(sa + BM * 128, &tmB, full_leader, kk + (seg == 0 ? p.npad : 0), zt * BN + (int)rank * (BN / 2), c);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
       }
@@ -898,6 +900,26 @@ k_item_mask(long long n_items, int gx, int nxt, int nzt, const double* __restric
 }
 
 
+// exact pruning: raster-ordered list of the (x tile, z tile) pairs with min key_z <= max key_x (see pairs.cu k_key_z);
+// item -> (xt, zt):  xg = item / (gx*nzt), r = item % (gx*nzt), zt = r / gx, xt = xg*gx + r % gx
+int fantasy_build_items(sbo_ctx* ctx, long long nx, long long nz, int tile_x, int tile_z, int gx, const double* key_x,
+                        const double* key_z, const long long** item_list, long long* n_list) {
+  const int nxt = (int)cdiv(nx, tile_x), nzt = (int)cdiv(nz, tile_z);
+  const long long n_raster = cdiv(nxt, gx) * gx * (long long)nzt;
+  SBO_TRY(sbo_ensure(ctx, ctx->tile_keys, sizeof(double) * (size_t)(nxt + nzt)));
+  double* qmax = (double*)ctx->tile_keys.p; double* rmin = qmax + nxt;
+  k_tile_keys<<<nxt, 256, 0, ctx->stream>>>(nx, tile_x, 1, key_x, qmax);
+  SBO_LAUNCH_CHECK();
+  k_tile_keys<<<nzt, 256, 0, ctx->stream>>>(nz, tile_z, 0, key_z, rmin);
+  SBO_LAUNCH_CHECK();
+  SBO_TRY(sbo_ensure(ctx, ctx->item_mask, sizeof(uint32_t) * (size_t)cdiv(n_raster, 32)));
+  k_item_mask<<<(unsigned)cdiv(n_raster, 256), 256, 0, ctx->stream>>>(n_raster, gx, nxt, nzt, qmax, rmin, (uint32_t*)ctx->item_mask.p);
+  SBO_LAUNCH_CHECK();
+  SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->item_mask.p, n_raster, ctx->item_list, n_list));
+  *item_list = (const long long*)ctx->item_list.p;
+  return SBO_OK;
+}
+
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
                    long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c,
                    const FantasyPruneArgs* pr) {
@@ -944,20 +966,8 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   const long long* item_list = nullptr;
   long long n_list = n_raster;
   const int* row_perm = pr ? pr->row_perm : nullptr;
-  if (pr && pr->key_x && pr->key_z) {
-    // exact pruning: only (x tile, z tile) pairs with min key_z <= max key_x can hold a newly-safe pair
-    SBO_TRY(sbo_ensure(ctx, ctx->tile_keys, sizeof(double) * (size_t)(nxt + nzt)));
-    double* qmax = (double*)ctx->tile_keys.p; double* rmin = qmax + nxt;
-    k_tile_keys<<<nxt, 256, 0, ctx->stream>>>(nx, tile_x, 1, pr->key_x, qmax);
-    SBO_LAUNCH_CHECK();
-    k_tile_keys<<<nzt, 256, 0, ctx->stream>>>(nz, tile_z, 0, pr->key_z, rmin);
-    SBO_LAUNCH_CHECK();
-    SBO_TRY(sbo_ensure(ctx, ctx->item_mask, sizeof(uint32_t) * (size_t)cdiv(n_raster, 32)));
-    k_item_mask<<<(unsigned)cdiv(n_raster, 256), 256, 0, ctx->stream>>>(n_raster, gx, nxt, nzt, qmax, rmin, (uint32_t*)ctx->item_mask.p);
-    SBO_LAUNCH_CHECK();
-    SBO_TRY(compact_mask(ctx, (const uint32_t*)ctx->item_mask.p, n_raster, ctx->item_list, &n_list));
-    item_list = (const long long*)ctx->item_list.p;
-  }
+  if (pr && pr->key_x && pr->key_z)
+    SBO_TRY(fantasy_build_items(ctx, nx, nz, tile_x, tile_z, gx, pr->key_x, pr->key_z, &item_list, &n_list));
   if (pr && pr->items_run) *pr->items_run = n_list * (long long)tile_x * tile_z;   // pairs per constraint actually evaluated
   ev_end(ctx);            // record prep = phase 6
   ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)

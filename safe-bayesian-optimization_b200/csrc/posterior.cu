@@ -406,12 +406,13 @@ static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, i
 }
 
 // Points per chunk.  The cross-covariance tile Kx[G][npad][P] is produced by k_crosscov and consumed by the solve kernel
-// of the same chunk; sized to stay resident in the 126 MB L2 (option "posterior_chunk_mb", default 48 MB) it never
-// makes the round trip through HBM that a 1 GiB scratch did (ncu r01: 16 GB written + 17 GB read at C4).  Never fewer
-// points than one full wave of the solve kernel needs (2 CTAs of 64 points per SM and GP).
+// of the same chunk (option "posterior_chunk_mb", default 1024).  Measured at C4 (profiles/r02_posterior_chunk_ab.txt):
+// L2-resident chunks (24-96 MB) avoid the HBM round trip of the tile but cost more than they save -- 11-18 launches
+// of partial waves instead of one: crosscov 8.3 -> 28 ms, solve 40 -> 44 ms -- so the large chunk stays the default.
+// Never fewer points than one full wave of the solve kernel needs (2 CTAs of 64 points per SM and GP).
 static long long chunk_points(const sbo_ctx* ctx, const ModelSpec& ms, long long count) {
   const size_t per_pt = (size_t)ms.G * ms.npad * sizeof(double);
-  const long long mb = ctx->opt_posterior_chunk_mb > 0 ? ctx->opt_posterior_chunk_mb : 48;
+  const long long mb = ctx->opt_posterior_chunk_mb > 0 ? ctx->opt_posterior_chunk_mb : 1024;
   long long p = (long long)((size_t)mb << 20) / (long long)per_pt;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);

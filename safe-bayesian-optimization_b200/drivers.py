@@ -34,10 +34,24 @@ def safeopt_iteration(GP_m, require_lipschitz_ucb=False):
         ok = np.all(np.isfinite(expander)) and any(GP_m.ucb(expander, j) >= 0. for j in range(1, GP_m.n_fun))
         take_minimizer = not ok
     x_new = minimizer if take_minimizer else expander
+    if not np.all(np.isfinite(x_new)):            # the other candidate may still exist (empty minimiser or expander set)
+        x_new = expander if take_minimizer else minimizer
+    _require_point(x_new, "SafeOpt: the safe set is empty on the grid (no minimiser and no expander)")
     return np.asarray(x_new, dtype=np.float64), {
         "minimizer": np.asarray(minimizer), "std_minimizer": float(std_minimizer),
         "expander": np.asarray(expander), "std_expander": float(std_expander),
         "chose": "minimizer" if take_minimizer else "expander", "acquisition_seconds": dt}
+
+
+class EmptySafeSet(RuntimeError):
+    """No grid point satisfies the safety constraints: there is nothing safe to sample.  The reference's DE always
+    returns SOME point inside the bounds (feasible or not); sampling a non-finite point would poison the
+    normalisation and the Cholesky factor of every later iteration, so the drivers stop instead."""
+
+
+def _require_point(x, msg):
+    if not np.all(np.isfinite(np.asarray(x, dtype=np.float64))):
+        raise EmptySafeSet(msg)
 
 
 def goose_iteration(GP_m):
@@ -53,6 +67,7 @@ def goose_iteration(GP_m):
         x_new = GP_m.explore_safeset(x_target)
         chose = "explore"
     dt = time.perf_counter() - t0
+    _require_point(x_new, "GoOSE: the safe set is empty on the grid (no safe minimum and no reachable target)")
     return np.asarray(x_new, dtype=np.float64), {
         "x_safe_min": np.asarray(x_safe_min), "min_safe_lcb": float(min_safe_lcb), "x_target": np.asarray(x_target),
         "target_lcb": float(target_lcb), "chose": chose, "acquisition_seconds": dt}

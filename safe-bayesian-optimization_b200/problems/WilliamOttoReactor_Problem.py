@@ -35,7 +35,9 @@ class WilliamOttoReactor:
     def __init__(self, measure_disturbance=False):
         self.rng = np.random.default_rng(42)          # reference: jax.random.PRNGKey(42)
         self.measure_disturbance = measure_disturbance
-        self._z = 0.0                                 # the current clipped standard-normal draw
+        # the reference draws jax.random.normal(PRNGKey(42)'s subkey) at construction (:13-15): with noise > 0 the first
+        # evaluations are disturbed even before noise_generator() is called.  Same behaviour, NumPy generator.
+        self._z = float(np.clip(self.rng.normal(), -2.05, 2.05))
 
     def noise_generator(self):
         """Draw the next disturbance sample (clipped to +-2.05 as in the reference, :48)."""
