@@ -469,7 +469,9 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             pr = rl["target"] if goose else rl["expander"]
-            lip["goose" if goose else "safeopt"] = {"ms_per_step": float(t[0]) * 1e3, "pairs": int(pr["pairs_algorithmic"]),
+            phl = eng.phase_ms()
+            lip["goose" if goose else "safeopt"] = {"ms_per_step": float(t[0]) * 1e3, "phase_ms_rank0": {k: round(v, 3) for k, v in phl.items()},
+                                                    "kernel_ms_rank0": round(sum(phl.values()), 3), "pairs": int(pr["pairs_algorithmic"]),
                                                     "pairs_evaluated": int(pr["pairs_evaluated"]), "n_hit": int(pr["n_hit"]),
                                                     "x_new_idx": int(rl["x_new_idx"])}
         lip["note"] = ("end-to-end wall time (host buffers) of one acquisition step with the reference's Lipschitz pair test "

@@ -157,7 +157,7 @@ int sbo_stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta,
  *   constraint idx (the reference passes L_{G-1} for every idx, SafeOpt.py:110).
  * Fantasy mode (north_star, not in the reference): rank-1 posterior update of every constraint GP with
  *   the observation ucb_i(x); z is newly safe if every updated lcb_i(z) >= 0; g(x) = #newly-safe z.
- *   precision: FP64 (SIMT reference kernel), TF32 (tcgen05/TMEM GEMM, FP32 accumulate) or TF32X3
+ *   precision: FP64 (FP64 tensor cores: DMMA mma.sync.m8n8k4.f64 tiles), TF32 (tcgen05/TMEM GEMM, FP32 accumulate) or TF32X3
  *   (same kernel over split operands: x_hi.z_hi + x_hi.z_lo + x_lo.z_hi).
  */
 typedef struct sbo_pair_result {
@@ -247,6 +247,7 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
  *                        Cauchy-Schwarz keys of csrc/pairs.cu (k_key_x / k_key_z) and only tile pairs whose keys can meet
  *                        are evaluated; FP64 counts are unchanged | 0: every pair goes through the GEMM
  *   "prior_mean_zero"    1: zero prior mean for every GP at the next sbo_set_model (GP_Robust.py, StableOpt) | 0 (default) GP_Safe.py:331
+ *   "fantasy_f64_variant" 1 (default): FP64 fantasy expander on the FP64 tensor cores (DMMA tiles) | 0: SIMT reference kernel
  *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);
 /* ---- hyper-parameter fit:  GP.negative_loglikelihood  (GP_Safe.py:169-192), batched ------

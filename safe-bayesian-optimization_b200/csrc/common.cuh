@@ -175,6 +175,7 @@ struct sbo_ctx {
                                      // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
   int64_t opt_posterior_chunk_mb = 0; // Kx scratch per chunk in MB (0 = default 48: L2 resident)
   int64_t opt_prior_mean_zero = 0;    // 1: zero prior mean for every GP (GP_Robust.py:322-323, StableOpt); 0: GP_Safe.py:331-332
+  int64_t opt_fantasy_f64_variant = 1; // FP64 fantasy expander: 1 (default) tensor cores (DMMA 128x64 tiles) | 0 SIMT reference kernel
   int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles
   int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };

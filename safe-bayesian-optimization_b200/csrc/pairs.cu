@@ -700,6 +700,167 @@ k_fantasy_f64(FantasyConsts fc, long long nx, long long nz, long long nxp, long 
   }
 }
 
+
+// =============================================================================================
+// Fantasy mode, FP64 on the tensor cores (north_star "FP64 tensor-core mode"; sm_100a has no FP64 tcgen05 path, so this
+// is DMMA, mma.sync.m8n8k4.f64, as in the posterior solve).  CTA = 128 candidates x 64 unsafe points, 8 warps of 32 x 32,
+// K chunks of 16 through a 3-stage cp.async ring (row stride 20 doubles: conflict-free fragment loads), 2 CTAs per SM.
+// Both operands are K-major rows (Vx[c][x][k], Vz[c][z][k]), which is exactly the row.col fragment layout.  Per
+// constraint: acc = v_x . v_z, then the same FP64 epilogue as k_fantasy_f64 (identical operations and order, so the two
+// kernels agree bit for bit up to the summation order of the dot product); the decision bits are ANDed over the
+// constraints in registers and counted per candidate with two shuffles + one atomicAdd.  Work items come from the same
+// exact-pruning list as the tcgen05 kernels (fantasy_build_items).
+// =============================================================================================
+#define FD_BM 128
+#define FD_BN 64
+#define FD_BK 16
+#define FD_LD 20
+#define FD_STAGES 3
+#define FD_STAGE_D ((FD_BM + FD_BN) * FD_LD)
+
+struct DmmaArgs {
+  long long nx, nz, nxp, nzp, n_items;
+  int np, nxt, nzt, gx;
+  const double *Vx, *Vz, *xn, *ax, *bx, *zn, *mz, *sz;
+  int* counts;
+  const int* row_perm;
+  const long long* item_list;
+};
+
+__device__ __forceinline__ void fd_cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fd_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, 2)
+k_fantasy_dmma(FantasyConsts fc, DmmaArgs a) {
+  extern __shared__ __align__(16) double fsm[];
+  const int RC = D + 2 * fc.nc;                       // constants per row / column: xn[D] | a[nc] | b[nc]  (zn | m | s)
+  double* rowc = fsm + FD_STAGES * FD_STAGE_D;        // [FD_BM][RC]
+  double* colc = rowc + FD_BM * RC;                   // [FD_BN][RC]
+  const long long item = a.item_list ? a.item_list[blockIdx.x] : (long long)blockIdx.x;
+  const long long per_group = (long long)a.gx * a.nzt;
+  const int xg = (int)(item / per_group), rr = (int)(item % per_group);
+  const int zt = rr / a.gx, xt = xg * a.gx + rr % a.gx;
+  if (xt >= a.nxt) return;
+  const long long xb = (long long)xt * FD_BM, zb = (long long)zt * FD_BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int wr = warp & 3, wp = warp >> 2;
+  const int np = a.np, nc = fc.nc;
+  for (int e = tid; e < FD_BM * RC; e += 256) {
+    const int r = e / RC, k = e - r * RC;
+    const long long xi = xb + r;
+    double v = 0.0;
+    if (xi < a.nx) v = k < D ? a.xn[(size_t)k * a.nx + xi] : (k < D + nc ? a.ax[(size_t)(k - D) * a.nx + xi] : a.bx[(size_t)(k - D - nc) * a.nx + xi]);
+    rowc[e] = v;
+  }
+  for (int e = tid; e < FD_BN * RC; e += 256) {
+    const int r = e / RC, k = e - r * RC;
+    const long long zi = zb + r;
+    double v = 0.0;
+    if (zi < a.nz) v = k < D ? a.zn[(size_t)k * a.nz + zi] : (k < D + nc ? a.mz[(size_t)(k - D) * a.nz + zi] : a.sz[(size_t)(k - D - nc) * a.nz + zi]);
+    colc[e] = v;
+  }
+  uint32_t okbits = 0xffffffffu;                      // bit (i*4 + j)*2 + e
+  const int nk = np / FD_BK;
+  for (int c = 0; c < nc; ++c) {
+    const double* Xg = a.Vx + ((size_t)c * a.nxp + xb) * np;
+    const double* Zg = a.Vz + ((size_t)c * a.nzp + zb) * np;
+    auto load_chunk = [&](int stage, int k0) {
+      double* Xs = fsm + stage * FD_STAGE_D;
+      double* Zs = Xs + FD_BM * FD_LD;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {                   // 128 rows x 16 doubles = 1024 x 16 B
+        const int e = tid + 256 * q, r = e >> 3, c2 = (e & 7) * 2;
+        fd_cp16(Xs + r * FD_LD + c2, Xg + (size_t)r * np + k0 + c2);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {                   // 64 rows x 16 doubles = 512 x 16 B
+        const int e = tid + 256 * q, r = e >> 3, c2 = (e & 7) * 2;
+        fd_cp16(Zs + r * FD_LD + c2, Zg + (size_t)r * np + k0 + c2);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    __syncthreads();                                   // constants visible; stages free (previous constraint finished)
+    load_chunk(0, 0);
+    if (nk > 1) load_chunk(1, FD_BK);
+    for (int kc = 0; kc < nk; ++kc) {
+      if (kc + 2 < nk) {
+        load_chunk((kc + 2) % FD_STAGES, (kc + 2) * FD_BK);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+      } else if (kc + 1 < nk) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const double* Xs = fsm + (kc % FD_STAGES) * FD_STAGE_D;
+      const double* Zs = Xs + FD_BM * FD_LD;
+#pragma unroll
+      for (int k0 = 0; k0 < FD_BK; k0 += 4) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = Xs[(wr * 32 + i * 8 + grp) * FD_LD + k0 + tig];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = Zs[(wp * 32 + j * 8 + grp) * FD_LD + k0 + tig];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) fd_dmma(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+      }
+      __syncthreads();                                 // the stage is refilled two iterations later
+    }
+    // epilogue of constraint c: acc[i][j][e] = v_x . v_z for x row wr*32+i*8+grp, z column wp*32+j*8+2*tig+e
+    const double sf2 = fc.sf2[c], beta = fc.beta;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double* rx = rowc + (wr * 32 + i * 8 + grp) * RC;
+      const double a_x = rx[D + c], b_x = rx[D + nc + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double* cz = colc + (wp * 32 + j * 8 + 2 * tig + e) * RC;
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) { const double df = cz[k] - rx[k]; s += df * df * fc.inv_ell[c][k]; }
+          const double cc = sf2 * exp(-0.5 * s) - acc[i][j][e];
+          const double mu = cz[D + c] + cc * a_x;
+          const double s2 = cz[D + nc + c] - cc * cc * b_x;
+          if (!((mu - beta * sqrt(fmax(s2, 0.0))) >= 0.0)) okbits &= ~(1u << ((i * 4 + j) * 2 + e));
+        }
+    }
+  }
+  // per candidate: newly-safe z of this tile = set bits of its row over valid columns, summed over the 4 lanes of a
+  // quad (tig) here and over the two column warps by the atomics
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (((okbits >> ((i * 4 + j) * 2 + e)) & 1u) && zb + wp * 32 + j * 8 + 2 * tig + e < a.nz) ++cnt;
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    const long long xi = xb + wr * 32 + i * 8 + grp;
+    if (tig == 0 && cnt && xi < a.nx) atomicAdd(a.counts + (a.row_perm ? a.row_perm[xi] : xi), cnt);
+  }
+}
+
+int fantasy_build_items(sbo_ctx* ctx, long long nx, long long nz, int tile_x, int tile_z, int gx, const double* key_x,
+                        const double* key_z, const long long** item_list, long long* n_list);
+
 struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run; };
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
                    long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c,
@@ -980,8 +1141,34 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     const double* key_x = ps.sorted ? (const double*)ctx->key_x.p : nullptr;
     const double* key_z = ps.sorted ? (const double*)ctx->key_z.p : nullptr;
     const int* row_perm = ps.sorted ? (const int*)ctx->perm_x.p : nullptr;
-    if (ps.precision == SBO_PREC_FP64) {
+    if (ps.precision == SBO_PREC_FP64 && ctx->opt_fantasy_f64_variant == 1) {
+      // FP64 tensor cores (DMMA): 128 x 64 tiles over the exact-pruning item list
+      DmmaArgs da{};
+      da.nx = nx; da.nz = nz; da.nxp = nxp; da.nzp = nzp; da.np = ms.npad;
+      da.nxt = (int)cdiv(nx, FD_BM); da.nzt = (int)cdiv(nz, FD_BN); da.gx = 32;
+      da.Vx = (const double*)ctx->vx.p; da.Vz = (const double*)ctx->vz.p;
+      da.xn = xn; da.ax = ax; da.bx = bx; da.zn = zn; da.mz = mz; da.sz = sz;
+      da.counts = cnt; da.row_perm = row_perm;
+      da.n_items = cdiv(da.nxt, da.gx) * da.gx * (long long)da.nzt;
+      ev_begin(ctx, 6);
+      if (key_x && key_z) SBO_TRY(fantasy_build_items(ctx, nx, nz, FD_BM, FD_BN, da.gx, key_x, key_z, &da.item_list, &da.n_items));
+      ev_end(ctx);
+      SBO_REQUIRE(da.n_items < 2147483647LL, "too many tile pairs for one launch");
+      const int RC = d + 2 * nc;
+      const size_t smem = sizeof(double) * ((size_t)FD_STAGES * FD_STAGE_D + (size_t)(FD_BM + FD_BN) * RC);
+      ev_begin(ctx, 4);
+      if (da.n_items > 0) {
+#define FDL(DD) do { SBO_CUDA(cudaFuncSetAttribute(k_fantasy_dmma<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                     k_fantasy_dmma<DD><<<(unsigned)da.n_items, 256, smem, ctx->stream>>>(fc, da); } while (0)
+        switch (d) { case 1: FDL(1); break; case 2: FDL(2); break; case 3: FDL(3); break; case 4: FDL(4); break;
+                     case 5: FDL(5); break; case 6: FDL(6); break; case 7: FDL(7); break; default: FDL(8); break; }
+#undef FDL
+        SBO_LAUNCH_CHECK();
+      }
+      ps.pairs_evaluated = da.n_items * (long long)FD_BM * FD_BN * nc;
+    } else if (ps.precision == SBO_PREC_FP64) {
       dim3 grid((unsigned)cdiv(nz, FB), (unsigned)cdiv(nx, FB));
+
       SBO_REQUIRE(grid.y <= 65535, "too many candidates for the FP64 fantasy kernel");
       ev_begin(ctx, 4);
 #define FL(DD) k_fantasy_f64<DD><<<grid, 256, 0, ctx->stream>>>(fc, nx, nz, nxp, nzp, (const double*)ctx->vx.p, (const double*)ctx->vz.p, xn, ax, bx, zn, mz, sz, cnt, key_x, key_z, row_perm, ctr)

@@ -39,3 +39,33 @@ def test_prune_is_exact(engine, oracle, c3, precision):
         assert full["n_z"] == pruned["n_z"] and full["pairs_algorithmic"] == pruned["pairs_algorithmic"]
         assert pruned["pairs_evaluated"] <= full["pairs_evaluated"]
         print(f"prune {precision}: pairs evaluated {pruned['pairs_evaluated']} of {full['pairs_evaluated']}, newly-safe total {int(full['counts'].sum())}")
+
+
+def test_fp64_tensor_core_kernel_matches_the_simt_kernel(engine):
+    """FP64 fantasy expander: the DMMA (mma.sync.m8n8k4.f64) tile kernel against the SIMT reference kernel, with and
+    without the exact pruning, ragged tile edges included (d = 2, 3, 4, 6; n not a multiple of the K chunk)."""
+    from sbo_b200 import _capi as capi, workloads
+    prec, keep_v = capi.PRECISIONS["fp64"]
+    for (d, ppd, n, G) in [(2, 41, 37, 2), (3, 14, 70, 3), (4, 9, 200, 4), (6, 5, 130, 3)]:
+        ds, lo, hi, pts, beta = workloads.small(d=d, pts_per_dim=ppd, n=n, seed=20 + d, G=G)
+        engine.set_model(ds)
+        engine.set_grid(lo, hi, pts)
+        engine.posterior(keep_v=keep_v, fetch=False)
+        engine.sets(beta, capi.UNSAFE_ANY)
+        res = {}
+        try:
+            for variant in (0, 1):
+                for prune in (0, 1):
+                    engine.set_option("fantasy_f64_variant", variant)
+                    engine.set_option("fantasy_prune", prune)
+                    res[(variant, prune)] = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+        finally:
+            engine.set_option("fantasy_f64_variant", 1)
+            engine.set_option("fantasy_prune", 1)
+        ref = res[(0, 0)]
+        for k, r in res.items():
+            # the two kernels sum the dot product in different orders: a pair exactly on the threshold may flip
+            dd = np.abs(r["counts"].astype(np.int64) - ref["counts"])
+            assert dd.sum() <= 2, (d, k, int(dd.sum()))
+            assert r["n_x"] == ref["n_x"] and r["n_z"] == ref["n_z"]
+        print(f"fp64 dmma d={d} n={n}: newly-safe {int(ref['counts'].sum())}, pairs evaluated {res[(1, 1)]['pairs_evaluated']} of {ref['pairs_algorithmic']}")
