@@ -141,7 +141,7 @@ struct sbo_ctx {
   DevBuf pts;
   // posterior (local shard)
   bool have_post = false, have_grad = false;   // have_grad: the last posterior accumulated the Lipschitz constants
-  DevBuf mean, var, kx, lmax;
+  DevBuf mean, var, kx, lmax, tabs;     // tabs: separable SE-ARD factor tables of the meshgrid (posterior.cu)
   int keep_v = 0;            // 0 none, 1 fp64, 2 fp32
   DevBuf vall;               // [(G-1)][count][npad] rows of V for the constraints
   // sets
@@ -173,6 +173,8 @@ struct sbo_ctx {
   long long n_unsafe_local = 0;
   int64_t opt_fantasy_variant = -1;  // -1 auto; bit 0: BN=256 (2 TMEM slots) instead of 128 (4 slots); bit 1: 8 epilogue warps;
                                      // bit 2: 2-CTA pairs (cta_group::2, 256x256 tile pairs)
+  int64_t opt_posterior_fused = 0;    // 1: meshgrid: separable factor tables + fused solve, no cross-covariance scratch (12 MB instead of 33.6 GB
+                                      // of DRAM traffic at C4, but 52.5 vs 40.0 ms: the table loads stall the DMMA loop) | 0 (default): two kernels + scratch
   int64_t opt_posterior_chunk_mb = 0; // Kx scratch per chunk in MB (0 = default 48: L2 resident)
   int64_t opt_prior_mean_zero = 0;    // 1: zero prior mean for every GP (GP_Robust.py:322-323, StableOpt); 0: GP_Safe.py:331-332
   int64_t opt_fantasy_f64_variant = 1; // FP64 fantasy expander: 1 (default) tensor cores (DMMA 128x64 tiles) | 0 SIMT reference kernel

@@ -17,6 +17,38 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Separable SE-ARD factors on a meshgrid.  k(x, X_j) = sf2 * prod_k exp(-1/2 (xn_k - Xn_jk)^2 / ell_k) and on a meshgrid
+// xn_k takes only pts_k values, so the cross-covariance of ANY grid point with training point j is a product of d table
+// entries  T[g][k][j][i_k]  (sf2 folded into the k = 0 table; rows j >= n are zero).  Tables: G * npad * sum_k pts_k
+// doubles (C4: 2 MB, C5: 6 MB) -- L2 resident -- built once per model upload.  With them the N x n cross-covariance
+// (GP_Safe.py:146-167 per point in the reference) is never written anywhere: the solve kernel multiplies it into its
+// shared-memory stage on the fly (k_solve_fused) and the mean / gradient kernel does the same in registers.
+// ---------------------------------------------------------------------------------------------
+struct TabSpec {
+  const double* base;             // nullptr: no tables (explicit points)
+  long long goff;                 // doubles per GP
+  long long koff[SBO_MAX_D];      // offset of axis k inside a GP's block
+  int pts[SBO_MAX_D];
+};
+__global__ void __launch_bounds__(256)
+k_build_tables(ModelSpec ms, GridSpec gs, TabSpec ts, double* __restrict__ tab) {
+  const int k = blockIdx.y, g = blockIdx.z;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tot = (long long)ms.npad * ts.pts[k];
+  if (e >= tot) return;
+  const int j = (int)(e / ts.pts[k]), i = (int)(e % ts.pts[k]);
+  double v = 0.0;
+  if (j < ms.n) {
+    const double xn = (axis_coord(gs, k, i) - ms.Xmean[k]) / ms.Xstd[k];      // GP_Safe.py:326
+    const double df = xn - ms.Xn[(size_t)j * ms.d + k];
+    v = exp(-0.5 * df * df * ms.inv_ell[g][k]);
+    if (k == 0) v *= ms.sf2[g];
+  }
+  tab[(size_t)g * ts.goff + ts.koff[k] + e] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1a: cross-covariance tile -> Kx scratch [G][npad][P] (points contiguous), mean, optional gradient
 // ---------------------------------------------------------------------------------------------
@@ -24,7 +56,7 @@ template <int D>
 __global__ void __launch_bounds__(XC_THREADS)
 k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __restrict__ Kx,
            double* __restrict__ mean_out, long long out_ld, double* __restrict__ gradmax,
-           double* __restrict__ grad_out, int grad_gp) {
+           double* __restrict__ grad_out, int grad_gp, TabSpec ts) {
   __shared__ double Xs[XC_JT * D];
   __shared__ double As[XC_JT];
   __shared__ double red[XC_THREADS / 32];
@@ -33,11 +65,19 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
   const bool in_chunk = pl < P;
   const bool ok = pl < valid;
   double xn[D];
+  const double* trow[D];          // table path: &T[g][k][0][i_k] of this point, row stride pts_k
+#pragma unroll
+  for (int k = 0; k < D; ++k) trow[k] = nullptr;
   if (ok) {
     double x[SBO_MAX_D];
-    point_coords(gs, shard_global(gs, p0 + pl), x);
+    const long long gp = shard_global(gs, p0 + pl);
+    point_coords(gs, gp, x);
 #pragma unroll
     for (int k = 0; k < D; ++k) xn[k] = (x[k] - ms.Xmean[k]) / ms.Xstd[k];       // GP_Safe.py:326
+    if (ts.base) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) trow[k] = ts.base + (size_t)blockIdx.y * ts.goff + ts.koff[k] + (gp / gs.stride[k]) % gs.pts[k];
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < D; ++k) xn[k] = 0.0;
@@ -68,7 +108,13 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
           double df[D];
 #pragma unroll
           for (int k = 0; k < D; ++k) { df[k] = xn[k] - Xs[j * D + k]; s += df[k] * df[k] * iell[k]; }
-          kv = sf2 * exp(-0.5 * s);                                              // GP_Safe.py:165-166
+          if (ts.base) {                                                         // product of the separable factors
+            kv = __ldg(trow[0] + (size_t)(j0 + j) * ts.pts[0]);
+#pragma unroll
+            for (int k = 1; k < D; ++k) kv *= __ldg(trow[k] + (size_t)(j0 + j) * ts.pts[k]);
+          } else {
+            kv = sf2 * exp(-0.5 * s);                                            // GP_Safe.py:165-166
+          }
           const double w = As[j] * kv;
           acc += w;
           if (want_grad) {
@@ -76,7 +122,7 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
             for (int k = 0; k < D; ++k) gk[k] += w * df[k];
           }
         }
-        kcol[(size_t)(j0 + j) * P] = kv;
+        if (Kx) kcol[(size_t)(j0 + j) * P] = kv;
       }
     }
   }
@@ -218,6 +264,7 @@ k_solve_var(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, in
 #define DV_KS 72   // Ks row stride (doubles): 72 = 8 mod 16
 #define DV_STAGE (DV_BM * DV_WS + DV_BK * DV_KS)
 #define DV_SMEM (2 * DV_STAGE * 8 + 4 * DV_BP * 8)
+#define DV_SMEM_F (DV_SMEM + SBO_MAX_D * DV_BP * 4)   // fused kernel: + per-point table offsets
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -349,28 +396,172 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
   }
 }
 
+// K1 fused (meshgrid): the same kernel, but the cross-covariance chunk Ks[32 training rows][64 points] is not read from a
+// scratch matrix: every thread multiplies the separable table factors of its 2 points x 4 rows straight into the
+// shared-memory stage (TabSpec).  No N x n matrix exists anywhere; DRAM traffic is the outputs plus the L2-resident
+// tables.  EMIT is a run-time argument here (it only steers the per-row-block epilogue).
+template <int D>
+__global__ void __launch_bounds__(256, 2)
+k_solve_fused(ModelSpec ms, GridSpec gs, TabSpec ts, int EMIT, long long p0, int valid,
+              double* __restrict__ var_out, long long out_ld, void* __restrict__ vall, long long v_count) {
+  extern __shared__ __align__(16) double dsm[];
+  double* red = dsm + 2 * DV_STAGE;                 // [4][DV_BP]
+  const int g = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, tig = lane & 3;
+  const int wr = warp & 3, wp = warp >> 2;          // warp tile: rows wr*32.., points wp*32..
+  const int np = ms.npad;
+  const double* Wg = ms.W + (size_t)g * np * np;
+  // table entry of point p of this CTA for training row j and axis k: tg[pidx[k][p] + j * pts_k]; the 32-bit offsets
+  // live in shared memory (the kernel has no registers to spare: 64 accumulators + fragments at 2 CTAs per SM)
+  const double* tg = ts.base + (size_t)g * ts.goff;
+  int* pidx = reinterpret_cast<int*>(red + 4 * DV_BP);          // [D][DV_BP]
+  for (int e = tid; e < D * DV_BP; e += 256) {
+    const int k = e / DV_BP, p = e - k * DV_BP;
+    const long long pl = (long long)blockIdx.x * DV_BP + p;
+    const long long gp = shard_global(gs, p0 + (pl < valid ? pl : 0));
+    pidx[e] = (int)(ts.koff[k] + (gp / gs.stride[k]) % gs.pts[k]);
+  }
+  __syncthreads();
+  const bool emit = (EMIT != 0) && (g > 0) && (vall != nullptr);
+  double ssum[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ssum[j][0] = ssum[j][1] = 0.0;
+
+  auto load_chunk = [&](int stage, int rb, int c0) {
+    double* Ws = dsm + stage * DV_STAGE;
+    double* Ks = Ws + DV_BM * DV_WS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {                   // W tile: 128 rows x 32 cols = 2048 x 16 B
+      const int e = tid + 256 * q;
+      const int r = e >> 4, c2 = (e & 15) * 2;
+      cp_async16(Ws + r * DV_WS + c2, Wg + (size_t)(rb * DV_BM + r) * np + c0 + c2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                   // cross-covariance tile: 32 training rows x 64 points, generated
+      const int r = warp + 8 * q;                   // (tid + 256 q) >> 5
+      const int j = c0 + r;
+      int2 o = *reinterpret_cast<const int2*>(pidx + 2 * lane);
+      double va = __ldg(tg + o.x + j * ts.pts[0]), vb = __ldg(tg + o.y + j * ts.pts[0]);
+#pragma unroll
+      for (int k = 1; k < D; ++k) {
+        o = *reinterpret_cast<const int2*>(pidx + k * DV_BP + 2 * lane);
+        va *= __ldg(tg + o.x + j * ts.pts[k]); vb *= __ldg(tg + o.y + j * ts.pts[k]);
+      }
+      *reinterpret_cast<double2*>(Ks + r * DV_KS + 2 * lane) = make_double2(va, vb);
+    }
+  };
+
+  const int nrb = np / DV_BM;
+  for (int rb = 0; rb < nrb; ++rb) {
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = (rb + 1) * DV_BM / DV_BK;
+    load_chunk(0, rb, 0);
+    for (int kc = 0; kc < nk; ++kc) {
+      if (kc + 1 < nk) {
+        load_chunk((kc + 1) & 1, rb, (kc + 1) * DV_BK);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const double* Ws = dsm + (kc & 1) * DV_STAGE;
+      const double* Ks = Ws + DV_BM * DV_WS;
+      // W is lower triangular: this warp's 32 rows need columns <= rb*128 + wr*32 + 31 only, i.e. K chunks
+      // kc <= rb*4 + wr; the later chunks of the diagonal block are all zeros for it
+      if (kc <= rb * (DV_BM / DV_BK) + wr)
+#pragma unroll
+      for (int k0 = 0; k0 < DV_BK; k0 += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = Ws[(wr * 32 + i * 8 + grp) * DV_WS + k0 + tig];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncthreads();
+    }
+    // row-block epilogue: acc[i][j][e] = v[row = rb*128 + wr*32 + i*8 + grp][point = wp*32 + j*8 + 2*tig + e]
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ssum[j][e] = fma(acc[i][j][e], acc[i][j][e], ssum[j][e]);
+        if (emit) {
+          const long long pl = (long long)blockIdx.x * DV_BP + wp * 32 + j * 8 + 2 * tig + e;
+          if (pl < valid) {
+            const size_t rowbase = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * DV_BM + wr * 32 + grp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double v = acc[i][j][e];
+              if (EMIT == 1) {
+                reinterpret_cast<double*>(vall)[rowbase + i * 8] = v;
+              } else if (EMIT == 2) {
+                reinterpret_cast<float*>(vall)[rowbase + i * 8] = to_tf32((float)v);
+              } else {
+                const float hi = to_tf32((float)v);
+                reinterpret_cast<float*>(vall)[rowbase + i * 8] = hi;
+                reinterpret_cast<float*>(vall)[rowbase + i * 8 + np] = to_tf32((float)(v - (double)hi));
+              }
+            }
+          }
+        }
+      }
+  }
+  // reduce |v|^2 over the 8 lanes that share a point (same tig, all grp) and over the 4 row warps
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double s = ssum[j][e];
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      if (grp == 0) red[wr * DV_BP + wp * 32 + j * 8 + 2 * tig + e] = s;
+    }
+  __syncthreads();
+  if (tid < DV_BP) {
+    const double s = red[tid] + red[DV_BP + tid] + red[2 * DV_BP + tid] + red[3 * DV_BP + tid];
+    const long long pl = (long long)blockIdx.x * DV_BP + tid;
+    if (pl < valid) {
+      const double v = fmax(0.0, ms.sf2[g] - s);                                  // GP_Safe.py:343
+      var_out[(size_t)g * out_ld + p0 + pl] = v * ms.Ystd[g] * ms.Ystd[g];        // :347
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
 template <int D>
 static void launch_crosscov(sbo_ctx* ctx, const GridSpec& gs, long long p0, int P, int valid, double* Kx,
-                            double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp) {
+                            double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp, const TabSpec& ts) {
   dim3 grid((unsigned)cdiv(P, XC_THREADS), (unsigned)ctx->ms.G);
   k_crosscov<D><<<grid, XC_THREADS, 0, ctx->stream>>>(ctx->ms, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax,
-                                                      grad_out, grad_gp);
+                                                      grad_out, grad_gp, ts);
 }
 
 static int crosscov_dispatch(sbo_ctx* ctx, const GridSpec& gs, long long p0, int P, int valid, double* Kx,
-                             double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp) {
+                             double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp,
+                             const TabSpec& ts = TabSpec{}) {
   switch (ctx->ms.d) {
-    case 1: launch_crosscov<1>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    case 2: launch_crosscov<2>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    case 3: launch_crosscov<3>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    case 4: launch_crosscov<4>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    case 5: launch_crosscov<5>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    case 6: launch_crosscov<6>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    case 7: launch_crosscov<7>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
-    default: launch_crosscov<8>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp); break;
+    case 1: launch_crosscov<1>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    case 2: launch_crosscov<2>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    case 3: launch_crosscov<3>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    case 4: launch_crosscov<4>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    case 5: launch_crosscov<5>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    case 6: launch_crosscov<6>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    case 7: launch_crosscov<7>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
+    default: launch_crosscov<8>(ctx, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax, grad_out, grad_gp, ts); break;
   }
   SBO_LAUNCH_CHECK();
   return SBO_OK;
@@ -405,6 +596,47 @@ static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, i
   return SBO_OK;
 }
 
+// K1 fused path (meshgrid grids, option "posterior_fused", default 1): separable factor tables, table-based mean /
+// gradient kernel (no Kx store), fused solve kernel (no Kx load).
+static int build_tables(sbo_ctx* ctx, TabSpec* ts) {
+  const ModelSpec& ms = ctx->ms;
+  const GridSpec& gs = ctx->gs;
+  *ts = TabSpec{};
+  long long tot = 0;
+  for (int k = 0; k < gs.d; ++k) { ts->koff[k] = tot; ts->pts[k] = (int)gs.pts[k]; tot += (long long)ms.npad * gs.pts[k]; }
+  ts->goff = tot;
+  SBO_TRY(sbo_ensure(ctx, ctx->tabs, sizeof(double) * (size_t)tot * ms.G));
+  ts->base = (const double*)ctx->tabs.p;
+  long long mx = 0;
+  for (int k = 0; k < gs.d; ++k) mx = mx > (long long)ms.npad * gs.pts[k] ? mx : (long long)ms.npad * gs.pts[k];
+  k_build_tables<<<dim3((unsigned)cdiv(mx, 256), gs.d, ms.G), 256, 0, ctx->stream>>>(ms, gs, *ts, (double*)ctx->tabs.p);
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
+template <int D>
+static void launch_fused(sbo_ctx* ctx, const TabSpec& ts, int emit, long long p0, int P, int valid, double* var_out, long long out_ld,
+                         void* vall, long long v_count) {
+  dim3 grid((unsigned)(P / DV_BP), (unsigned)ctx->ms.G);
+  cudaFuncSetAttribute(k_solve_fused<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM_F);
+  k_solve_fused<D><<<grid, 256, DV_SMEM_F, ctx->stream>>>(ctx->ms, ctx->gs, ts, emit, p0, valid, var_out, out_ld, vall, v_count);
+}
+static int fused_dispatch(sbo_ctx* ctx, const TabSpec& ts, int emit, long long p0, int P, int valid, double* var_out, long long out_ld,
+                          void* vall, long long v_count) {
+  switch (ctx->ms.d) {
+    case 1: launch_fused<1>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    case 2: launch_fused<2>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    case 3: launch_fused<3>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    case 4: launch_fused<4>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    case 5: launch_fused<5>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    case 6: launch_fused<6>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    case 7: launch_fused<7>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+    default: launch_fused<8>(ctx, ts, emit, p0, P, valid, var_out, out_ld, vall, v_count); break;
+  }
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
 // Points per chunk.  The cross-covariance tile Kx[G][npad][P] is produced by k_crosscov and consumed by the solve kernel
 // of the same chunk (option "posterior_chunk_mb", default 1024).  Measured at C4 (profiles/r02_posterior_chunk_ab.txt):
 // L2-resident chunks (24-96 MB) avoid the HBM round trip of the tile but cost more than they save -- 11-18 launches
@@ -435,8 +667,10 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   SBO_TRY(sbo_ensure(ctx, ctx->mean, sizeof(double) * (size_t)ms.G * count));
   SBO_TRY(sbo_ensure(ctx, ctx->var, sizeof(double) * (size_t)ms.G * count));
   SBO_TRY(sbo_ensure(ctx, ctx->lmax, sizeof(double) * SBO_MAX_G));
-  const long long P = chunk_points(ctx, ms, count);
-  SBO_TRY(sbo_ensure(ctx, ctx->kx, sizeof(double) * (size_t)ms.G * ms.npad * P));
+  // meshgrid + DMMA variant: fused path, no cross-covariance scratch at all (one "chunk" = the whole shard)
+  const bool fused = ctx->gs.kind == 1 && ctx->opt_posterior_variant == 1 && ctx->opt_posterior_fused;
+  const long long P = fused ? cdiv(count, 128) * 128 : chunk_points(ctx, ms, count);
+  if (!fused) SBO_TRY(sbo_ensure(ctx, ctx->kx, sizeof(double) * (size_t)ms.G * ms.npad * P));
   ctx->keep_v = 0;
   if (keep_v && ms.G > 1) {
     const size_t esz = keep_v == 1 ? sizeof(double) : (keep_v == 3 ? 2 * sizeof(float) : sizeof(float));
@@ -444,16 +678,25 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   }
   SBO_CUDA(cudaMemsetAsync(ctx->lmax.p, 0, sizeof(double) * SBO_MAX_G, ctx->stream));
   ev_reset(ctx, 1); ev_reset(ctx, 2);
+  TabSpec ts{};
+  if (fused) {
+    ev_begin(ctx, 1);
+    SBO_TRY(build_tables(ctx, &ts));
+    ev_end(ctx);
+  }
   for (long long p0 = 0; p0 < count; p0 += P) {
     const int valid = (int)((count - p0) < P ? (count - p0) : P);
     const int Pc = (int)P;
     ev_begin(ctx, 1);
-    SBO_TRY(crosscov_dispatch(ctx, ctx->gs, p0, Pc, valid, (double*)ctx->kx.p, (double*)ctx->mean.p, count,
-                              with_grad ? (double*)ctx->lmax.p : nullptr, nullptr, -1));
+    SBO_TRY(crosscov_dispatch(ctx, ctx->gs, p0, Pc, valid, fused ? nullptr : (double*)ctx->kx.p, (double*)ctx->mean.p, count,
+                              with_grad ? (double*)ctx->lmax.p : nullptr, nullptr, -1, ts));
     ev_end(ctx);
     ev_begin(ctx, 2);
-    SBO_TRY(solve_dispatch(ctx, (const double*)ctx->kx.p, Pc, p0, valid, (double*)ctx->var.p, count,
-                           (ms.G > 1) ? keep_v : 0, ctx->vall.p, count));
+    if (fused)
+      SBO_TRY(fused_dispatch(ctx, ts, (ms.G > 1) ? keep_v : 0, p0, Pc, valid, (double*)ctx->var.p, count, ctx->vall.p, count));
+    else
+      SBO_TRY(solve_dispatch(ctx, (const double*)ctx->kx.p, Pc, p0, valid, (double*)ctx->var.p, count,
+                             (ms.G > 1) ? keep_v : 0, ctx->vall.p, count));
     ev_end(ctx);
   }
   if (keep_v && ms.G > 1) ctx->keep_v = keep_v;
