@@ -304,9 +304,9 @@ def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
                 if world == 1:
                     return eng.safeopt_step(ds5, beta5, mode="fantasy", precision="tf32")
                 return sharded.safeopt_step(eng, ds5, beta5, mode="fantasy", precision="tf32")
+        eng.mem_peak(reset=True)
         step5()
         torch.cuda.synchronize()
-        free_min = torch.cuda.mem_get_info(dev)[0]
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
@@ -335,7 +335,7 @@ def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
                     "x_new_idx": int(r5["x_new_idx"]), "phase_ms_rank0": ph,
                     "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
                                  "kernel": "tc::k_fantasy_tc2 (tf32), per GPU, evaluated pairs only"},
-                    "device_mem_high_water_gb": (total - min(free_min, torch.cuda.mem_get_info(dev)[0])) / 2 ** 30,
+                    "device_mem_high_water_gb": eng.mem_peak() / 2 ** 30,
                     "device_mem_total_gb": total / 2 ** 30, "steps": 1, "warmup": 1})
         # parity at full size: this rank's posterior on a random sample of its shard against the FP64 oracle
         if rank == 0:
@@ -536,7 +536,8 @@ def run_ours(args):
             "config": {"workload": wl_name, "mode": args.mode, "precision": args.precision, "N": N, "n": n, "d": d, "G": G,
                        "beta": beta, "n_safe": int(res["n_safe"]), "n_unsafe": int(res["n_unsafe"]), "n_min": int(res["n_min"]),
                        "pairs": pairs, "pairs_evaluated": int(ex["pairs_evaluated"]), "n_hit": int(ex["n_hit"]), "x_new_idx": int(res["x_new_idx"]),
-                       "prune": int(args.prune), "value_counts": "all |S|*|Z|*(G-1) pairs: the exact pruning decides the skipped ones without evaluating them",
+                       "prune": int(args.prune), "refined_pairs_fp64": int(ex.get("n_ambiguous", 0)), "refined_safe": int(ex.get("n_refined_safe", 0)),
+                       "value_counts": "all |S|*|Z|*(G-1) pairs: the exact pruning decides the skipped ones without evaluating them",
                        "l2": "256 MiB flush buffer written between timed steps; working set >> L2",
                        "excludes": "plant evaluation and hyper-parameter fit (host side in the reference too)"},
             "phase_ms": ph, "clocks": clk, "gpu_launches": int(launches // max(1, args.steps)),

@@ -167,6 +167,7 @@ typedef struct sbo_pair_result {
   int64_t pairs_algorithmic;                     /* n_x * n_z * (constraints)         */
   int64_t pairs_evaluated;                       /* after tile-level early exit       */
   int64_t n_hit;                                 /* |expander set| (union over idx) or |target set| */
+  int64_t n_ambiguous, n_refined_safe;           /* fantasy TF32X3: pairs re-evaluated in FP64 / of those, newly safe (local shard) */
 } sbo_pair_result;
 int sbo_expander(sbo_ctx* ctx, int mode, int precision, double beta, const double* L /* G, lipschitz mode */,
                  sbo_pair_result* out, int32_t* counts /* count, fantasy mode, or NULL */);
@@ -235,8 +236,11 @@ int sbo_goose_step_sharded(sbo_ctx* ctx, double beta, int unsafe_rule, const dou
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this library launched on ctx since the last reset */
 int64_t sbo_kernel_launches(sbo_ctx* ctx, int reset);
+/* high-water mark (bytes) of the device memory held by the context's work buffers since the last reset */
+int64_t sbo_mem_peak(sbo_ctx* ctx, int reset);
 /* device time of named phases of the last calls, milliseconds (CUDA events on the ctx stream).
- * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce, 6 pair preparation */
+ * phase: 0 model, 1 posterior(crosscov), 2 posterior(solve), 3 sets, 4 pairs, 5 argreduce, 6 pair preparation,
+ *        7 FP64 refinement of the split-TF32 fantasy expander */
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
 /* tuning / diagnosis options (defaults reproduce the documented behaviour; none changes a result):
  *   "posterior_variant"  1 (default) FP64 tensor cores (DMMA) | 0 FP64 SIMT register tiles
@@ -250,6 +254,7 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
  *                        Cauchy-Schwarz keys of csrc/pairs.cu (k_key_x / k_key_z) and only tile pairs whose keys can meet
  *                        are evaluated; FP64 counts are unchanged | 0: every pair goes through the GEMM
  *   "prior_mean_zero"    1: zero prior mean for every GP at the next sbo_set_model (GP_Robust.py, StableOpt) | 0 (default) GP_Safe.py:331
+ *   "fantasy_refine"     1 (default): TF32X3 fantasy expander settles ambiguous pairs in FP64 (exact counts) | 0: decide on the FP32 value
  *   "fantasy_f64_variant" 1 (default): FP64 fantasy expander on the FP64 tensor cores (DMMA tiles) | 0: SIMT reference kernel
  *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);

@@ -21,7 +21,7 @@ PREC_FP64, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 PRECISIONS = {"fp64": (0, 1), "tf32": (1, 2), "tf32x3": (2, 3)}
 ARGMAX_VAR0, ARGMIN_LCB0, ARGMIN_UCB0, ARGMIN_DIST = 0, 1, 2, 3
 MASK_SAFE, MASK_MIN, MASK_UNSAFE, MASK_USER, MASK_EXPANDER, MASK_TARGET = 0, 1, 2, 3, 4, 5
-PHASES = ("model", "crosscov", "solve", "sets", "pairs", "argreduce", "pair_prep")
+PHASES = ("model", "crosscov", "solve", "sets", "pairs", "argreduce", "pair_prep", "refine")
 
 
 class SetsResult(C.Structure):
@@ -35,7 +35,8 @@ class PairResult(C.Structure):
     _fields_ = [("best_idx", C.c_int64), ("best_value", C.c_double),
                 ("per_idx", C.c_int64 * MAX_G), ("per_value", C.c_double * MAX_G),
                 ("n_x", C.c_int64), ("n_z", C.c_int64),
-                ("pairs_algorithmic", C.c_int64), ("pairs_evaluated", C.c_int64), ("n_hit", C.c_int64)]
+                ("pairs_algorithmic", C.c_int64), ("pairs_evaluated", C.c_int64), ("n_hit", C.c_int64),
+                ("n_ambiguous", C.c_int64), ("n_refined_safe", C.c_int64)]
 
 
 class StepResult(C.Structure):
@@ -96,6 +97,7 @@ SIGNATURES = {
     "sbo_safeopt_step_sharded": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.c_int, _D, C.POINTER(StepResult)]),
     "sbo_goose_step_sharded": (C.c_int, [_P, C.c_double, C.c_int, _D, C.POINTER(StepResult)]),
     "sbo_kernel_launches": (C.c_int64, [_P, C.c_int]),
+    "sbo_mem_peak": (C.c_int64, [_P, C.c_int]),
     "sbo_phase_ms": (C.c_int, [_P, C.c_int, _D]),
     "sbo_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "sbo_release": (C.c_int, [_P, C.c_int]),

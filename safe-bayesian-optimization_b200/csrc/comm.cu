@@ -150,7 +150,7 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
     }
   }
   SBO_TRY(pairs_import(ctx, n_total, rows, vrows));
-  if (big) { SBO_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(cm->vrows.p); cm->vrows.p = nullptr; cm->vrows.cap = 0; }
+  if (big) { SBO_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(cm->vrows.p); ctx->mem_now -= (int64_t)cm->vrows.cap; cm->vrows.p = nullptr; cm->vrows.cap = 0; }
   // (4) run on the local shard, combine the per-candidate results
   const size_t res_b = fantasy ? sizeof(int) * (size_t)n_total : (size_t)nc * (size_t)(goose ? info.n_z_local : n_total);
   SBO_TRY(sbo_ensure(ctx, cm->result, res_b ? res_b : 16));
@@ -163,10 +163,11 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   SBO_TRY(pairs_finish(ctx, goose ? 1 : 0, goose ? 0 : offset, cm->result.p, &loc, nullptr));
   // (5) global optima: per constraint (value, index), then the first best over the constraints (SafeOpt.py:120-122)
   const int nmask = fantasy ? 1 : nc;
-  const int nrec = 2 * SBO_MAX_G + 2;
-  double mine2[2 * SBO_MAX_G + 2];
+  const int nrec = 2 * SBO_MAX_G + 4;
+  double mine2[2 * SBO_MAX_G + 4];
   for (int c = 0; c < SBO_MAX_G; ++c) { mine2[2 * c] = loc.per_value[c]; mine2[2 * c + 1] = (double)loc.per_idx[c]; }
   mine2[2 * SBO_MAX_G] = (double)loc.n_hit; mine2[2 * SBO_MAX_G + 1] = (double)loc.pairs_evaluated;
+  mine2[2 * SBO_MAX_G + 2] = (double)loc.n_ambiguous; mine2[2 * SBO_MAX_G + 3] = (double)loc.n_refined_safe;
   SBO_TRY(gather_record(ctx, mine2, nrec, g));
   memset(pr, 0, sizeof(*pr));
   pr->best_idx = -1; pr->best_value = goose ? INFINITY : -INFINITY;
@@ -177,7 +178,10 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
       pr->best_idx = pr->per_idx[c]; pr->best_value = pr->per_value[c];
     }
   }
-  for (int r = 0; r < R; ++r) { pr->n_hit += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G]; pr->pairs_evaluated += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 1]; }
+  for (int r = 0; r < R; ++r) {
+    pr->n_hit += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G]; pr->pairs_evaluated += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 1];
+    pr->n_ambiguous += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 2]; pr->n_refined_safe += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 3];
+  }
   pr->n_x = n_total; pr->n_z = nz_total; pr->pairs_algorithmic = n_total * nz_total * nc;
   if (big) SBO_TRY(sbo_release(ctx, 2));
   return SBO_OK;

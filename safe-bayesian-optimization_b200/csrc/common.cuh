@@ -119,6 +119,7 @@ struct PairStage {
   long long seg_off[65] = {0};
   bool canon = false;
   long long nz_global = -1;
+  long long n_ambiguous = 0, n_refined_safe = 0;     // split-TF32 refinement statistics of the last run
 };
 
 struct sbo_comm;   // comm.cu: NCCL communicator + gathered buffers
@@ -130,6 +131,7 @@ struct sbo_ctx {
   bool own_stream = true;
   std::string err;
   int64_t launches = 0;
+  int64_t mem_now = 0, mem_peak = 0;   // device bytes held by the context's work buffers (sbo_ensure), and their high-water mark
 
   // model
   bool have_model = false;
@@ -159,6 +161,7 @@ struct sbo_ctx {
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
   DevBuf key_x, key_z, perm_x, perm_z, sort_ws, tile_keys, item_mask, item_list;   // exact pruning of the fantasy expander
+  DevBuf amb_list, amb_ctr, amb_mask, amb_xd, amb_zd, amb_rx, amb_rz, amb_pts, amb_vx, amb_vz;   // FP64 refinement of the split-TF32 expander
   DevBuf st_score, st_mask;               // StableOpt: per-x_c worst-case score and robust-safe bitmask
   DevBuf gz_mask, gz_idx, gz_pay;         // all-gathered unsafe set of a sharded Lipschitz expander
   PairStage ps;
@@ -178,6 +181,7 @@ struct sbo_ctx {
   int64_t opt_posterior_chunk_mb = 0; // Kx scratch per chunk in MB (0 = default 48: L2 resident)
   int64_t opt_prior_mean_zero = 0;    // 1: zero prior mean for every GP (GP_Robust.py:322-323, StableOpt); 0: GP_Safe.py:331-332
   int64_t opt_fantasy_f64_variant = 1; // FP64 fantasy expander: 1 (default) tensor cores (DMMA 128x64 tiles) | 0 SIMT reference kernel
+  int64_t opt_fantasy_refine = 1;     // split-TF32 fantasy expander: pairs the FP32 error bound cannot settle are re-evaluated in FP64 (exact counts)
   int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles
   int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };
@@ -227,6 +231,7 @@ int model_append(sbo_ctx* ctx, const double* x_norm_new, const double* y_norm_ne
 int stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value, int64_t* n_robust_safe, double* score_host);
 int nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll);
 int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v);
+int posterior_vrows_dev(sbo_ctx* ctx, long long m, const double* pts_dev, double* vout);
 int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, double* var);
 int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad);
 int sets_pass1(sbo_ctx* ctx, double beta, int rule, int strict, sbo_sets_result* out);

@@ -42,6 +42,12 @@ struct Params {
   unsigned int* sched_counter;   // zeroed before every launch
   const long long* item_list;    // feasible raster items in ascending order (exact pruning), or null = all n_items
   const int* row_perm;           // sorted candidate slot -> row of `counts` (null = identity)
+  // refinement (REFINE kernels): pairs whose decision the FP32 error bound cannot settle are NOT counted here but
+  // appended as (candidate slot, z column) to amb_list for the FP64 re-evaluation (pairs.cu k_refine_pairs)
+  int2* amb_list;
+  unsigned long long* amb_count;   // [0] entries appended (may exceed the capacity: overflow is detected by the host)
+  long long amb_cap;
+  float e_abs, d_mu, d_t;          // absolute error terms of the FP32 epilogue (covariance, mean, variance side)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,7 +168,7 @@ __device__ __forceinline__ void set_bit_if_safe(uint32_t& w, float mu, float mm,
 // row constants of one candidate for one constraint, duplicated into both halves of a packed pair
 template <int D4>
 struct RowConsts {
-  uint64_t xx[4 * D4], Cx, ax, nbx;
+  uint64_t xx[4 * D4], Cx, ax, nbx, ex;      // ex: sqrt(c1)*|v_x| (refinement band), duplicated like the others
   __device__ __forceinline__ void load(const float* __restrict__ rowrec_row) {
     const float4* rr = reinterpret_cast<const float4*>(rowrec_row);
 #pragma unroll
@@ -171,7 +177,7 @@ struct RowConsts {
       xx[4 * v] = pk2(t.x, t.x); xx[4 * v + 1] = pk2(t.y, t.y); xx[4 * v + 2] = pk2(t.z, t.z); xx[4 * v + 3] = pk2(t.w, t.w);
     }
     const float4 rt = __ldg(rr + D4);
-    Cx = pk2(rt.x, rt.x); ax = pk2(rt.y, rt.y); nbx = pk2(-rt.z, -rt.z);
+    Cx = pk2(rt.x, rt.x); ax = pk2(rt.y, rt.y); nbx = pk2(-rt.z, -rt.z); ex = pk2(rt.w, rt.w);
   }
 };
 
@@ -204,6 +210,52 @@ __device__ __forceinline__ uint32_t epilogue_chunk(const uint32_t (&acc)[32], co
     set_bit_if_safe(w, mu1, m1, t1, 2u << (2 * jp));
   }
   return w;
+}
+
+// Refining variant (split-TF32 mode).  E = ex*ez + e_abs bounds the error of the computed covariance (operand split,
+// one ulp of the running sum per tensor-core accumulation step, ex2.approx, FP32 records); d_mu / d_t bound the FP32
+// rounding of the mean and variance sides of the test.  The updated bound f(cov) = mu' - beta*sigma' is CONVEX in cov and
+// increasing for cov >= 0, so with lo = cov - E, hi = cov + E:
+//   U (settled unsafe)  <=  f is negative at lo AND at hi when evaluated OPTIMISTICALLY (+d_mu, -d_t): the maximum over the
+//                           interval is at an end;
+//   S (settled safe)    <=  lo >= 0 (monotone branch) and f is non-negative at lo evaluated PESSIMISTICALLY (-d_mu, +d_t).
+// Everything else is AMBIGUOUS and goes to the FP64 re-evaluation (pairs.cu refine_ambiguous).
+template <int D4>
+__device__ __forceinline__ void epilogue_chunk_refine(const uint32_t (&acc)[32], const uint64_t* __restrict__ rec, const RowConsts<D4>& rc,
+                                                      uint64_t e_abs2, uint64_t d_mu2, uint64_t d_t2, uint32_t& S, uint32_t& U) {
+  constexpr int RS = 4 * D4 + 4;
+  const uint64_t minus1 = pk2(-1.f, -1.f);
+  uint32_t wlo = 0, whi = 0, wsf = 0;
+#pragma unroll
+  for (int jp = 0; jp < 16; ++jp) {
+    const uint64_t* p = rec + jp * RS;
+    uint64_t e = add2(rc.Cx, p[4 * D4]);
+#pragma unroll
+    for (int k = 0; k < 4 * D4; ++k) e = fma2(rc.xx[k], p[k], e);
+    float e0, e1;
+    upk2(e, e0, e1);
+    const uint64_t ex = pk2(ex2_approx(e0), ex2_approx(e1));
+    const uint64_t a2 = pk2(__uint_as_float(acc[2 * jp]), __uint_as_float(acc[2 * jp + 1]));
+    const uint64_t cov = fma2(a2, minus1, ex);
+    const uint64_t E = fma2(rc.ex, p[4 * D4 + 3], e_abs2);                // ex*ez + e_abs
+    const uint64_t cl = fma2(E, minus1, cov), ch = add2(cov, E);
+    const uint64_t m_opt = add2(p[4 * D4 + 1], d_mu2), m_pes = fma2(d_mu2, minus1, p[4 * D4 + 1]);   // m_z +- d_mu
+    const uint64_t s_opt = fma2(d_t2, minus1, p[4 * D4 + 2]), s_pes = add2(p[4 * D4 + 2], d_t2);     // s'_z -+ d_t
+    const uint64_t cl2 = mul2(cl, cl), ch2 = mul2(ch, ch);
+    const uint64_t mu_lo = fma2(cl, rc.ax, m_opt), mu_hi = fma2(ch, rc.ax, m_opt), mu_sf = fma2(cl, rc.ax, m_pes);
+    const uint64_t t_lo = fma2(cl2, rc.nbx, s_opt), t_hi = fma2(ch2, rc.nbx, s_opt), t_sf = fma2(cl2, rc.nbx, s_pes);
+    const uint64_t mm_lo = mul2(mu_lo, mu_lo), mm_hi = mul2(mu_hi, mu_hi), mm_sf = mul2(mu_sf, mu_sf);
+    float a0, a1, b0, b1, c0, c1, l0, l1;
+    upk2(mu_lo, a0, a1); upk2(t_lo, b0, b1); upk2(mm_lo, c0, c1);
+    set_bit_if_safe(wlo, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wlo, a1, c1, b1, 2u << (2 * jp));
+    upk2(mu_hi, a0, a1); upk2(t_hi, b0, b1); upk2(mm_hi, c0, c1);
+    set_bit_if_safe(whi, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(whi, a1, c1, b1, 2u << (2 * jp));
+    upk2(mu_sf, a0, a1); upk2(t_sf, b0, b1); upk2(mm_sf, c0, c1); upk2(cl, l0, l1);
+    a0 = l0 < 0.f ? l0 : a0; a1 = l1 < 0.f ? l1 : a1;                     // lo < 0: not on the monotone branch -> never "settled safe"
+    set_bit_if_safe(wsf, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wsf, a1, c1, b1, 2u << (2 * jp));
+  }
+  S = wsf;
+  U = ~wlo & ~whi;
 }
 
 // work item = one (x tile, z tile) pair, all constraints.  Items are ordered so that a group of GX x tiles sweeps
@@ -531,7 +583,7 @@ __device__ __forceinline__ bool item_coords2(const Params& p, long long item, in
   return xt < p.nxt;
 }
 
-template <int D4, int EW>
+template <int D4, int EW, bool REFINE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg2<D4>;
@@ -693,9 +745,11 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int xt, zt;
       if (!item_coords2(p, item, xt, zt)) continue;
       const long long xrow = (long long)xt * 2 * BM + (long long)rank * BM + row;
-      uint32_t bits[NCH];
+      uint32_t bits[NCH];              // REFINE: safe at lo/mid/hi for every constraint so far
+      uint32_t ubits[NCH];             // REFINE: unsafe at lo and hi for some constraint
 #pragma unroll
-      for (int h = 0; h < NCH; ++h) bits[h] = 0xffffffffu;
+      for (int h = 0; h < NCH; ++h) { bits[h] = 0xffffffffu; ubits[h] = 0u; }
+      const uint64_t e_abs2 = pk2(p.e_abs, p.e_abs), d_mu2 = pk2(p.d_mu, p.d_mu), d_t2 = pk2(p.d_t, p.d_t);
       for (int c = 0; c < p.nc; ++c) {
         RowConsts<D4> rc;
         rc.load(p.rowrec + ((size_t)c * p.nxp + xrow) * RS);
@@ -710,7 +764,13 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           uint32_t r[32];
           tmem_ld32(taddr + h * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          bits[h] &= epilogue_chunk<D4>(r, cb + (size_t)h * 16 * RS, rc);
+          if (REFINE) {
+            uint32_t S, U;
+            epilogue_chunk_refine<D4>(r, cb + (size_t)h * 16 * RS, rc, e_abs2, d_mu2, d_t2, S, U);
+            bits[h] &= S; ubits[h] |= U;
+          } else {
+            bits[h] &= epilogue_chunk<D4>(r, cb + (size_t)h * 16 * RS, rc);
+          }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -722,6 +782,23 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
       for (int h = 0; h < NCH; ++h) cnt += __popc(bits[h]);
       if (xrow < p.nx && cnt) atomicAdd(p.counts + (p.row_perm ? p.row_perm[xrow] : xrow), cnt);
+      if (REFINE && xrow < p.nx) {
+#pragma unroll
+        for (int h = 0; h < NCH; ++h) {
+          uint32_t amb = ~bits[h] & ~ubits[h];              // neither settled safe nor settled unsafe
+          if (amb) {
+            const int n = __popc(amb);
+            const unsigned long long base = atomicAdd(p.amb_count, (unsigned long long)n);
+            const int zc0 = zt * BN + (half * NCH + h) * 32;
+            unsigned long long w = base;
+            while (amb) {
+              const int bpos = __ffs(amb) - 1; amb &= amb - 1;
+              if ((long long)w < p.amb_cap) p.amb_list[w] = make_int2((int)xrow, zc0 + bpos);
+              ++w;
+            }
+          }
+        }
+      }
     }
   }
   // ---- teardown: neither CTA may exit (or free TMEM) while the other can still signal it
@@ -744,7 +821,7 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 template <int D4>
 __global__ void __launch_bounds__(256)
 k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, const double* __restrict__ coords,
-             const double* __restrict__ a, const double* __restrict__ b, float* __restrict__ rec) {
+             const double* __restrict__ a, const double* __restrict__ b, float* __restrict__ rec, double esc) {
   constexpr int RS = 4 * D4 + 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
@@ -776,7 +853,9 @@ k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, cons
     o[(4 * D4 + 1) * st] = (float)av;
     o[(4 * D4 + 2) * st] = (float)(fc.beta * fc.beta * bv);
   }
-  o[(4 * D4 + 3) * st] = 0.f;
+  // refinement band: sqrt(c1)*|v|, |v|^2 = sf2 - sigma^2 (rows: sigma^2 = 1/b - sn2; columns: b holds sigma^2); rounded UP
+  const double s2 = is_row ? (1.0 / bv - fc.sn2[c]) : bv;
+  o[(4 * D4 + 3) * st] = esc > 0.0 ? __double2float_ru(esc * sqrt(fmax(fc.sf2[c] - s2, 0.0))) : 0.f;
 }
 
 static int make_map(sbo_ctx* ctx, CUtensorMap* map, const float* base, int rowlen, long long rows, int nc, int box_rows) {
@@ -834,10 +913,12 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
   return SBO_OK;
 }
 
-template <int D4, int EW>
+struct RefineArgs { int2* list; unsigned long long* count; long long cap; float e_abs, d_mu, d_t; };
+
+template <int D4, int EW, bool REFINE>
 static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
                    const float* Vx, const float* Vz, const float* rowrec, const float* colrec, int* counts, int* err,
-                   const long long* item_list, long long n_list, const int* row_perm, int gx) {
+                   const long long* item_list, long long n_list, const int* row_perm, int gx, const RefineArgs& ra) {
   using C = Cfg2<D4>;
   CUtensorMap tmA, tmB;
   const int rowlen = split ? 2 * fc.npad : fc.npad;
@@ -856,10 +937,11 @@ static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
   p.sched_counter = (unsigned int*)(err + 1);
   p.item_list = item_list; p.row_perm = row_perm;
+  p.amb_list = ra.list; p.amb_count = ra.count; p.amb_cap = ra.cap; p.e_abs = ra.e_abs; p.d_mu = ra.d_mu; p.d_t = ra.d_t;
   if (p.n_items == 0) return SBO_OK;
-  SBO_CUDA(cudaFuncSetAttribute(k_fantasy_tc2<D4, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  SBO_CUDA((cudaFuncSetAttribute(k_fantasy_tc2<D4, EW, REFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
   const int grid = 2 * (int)((p.n_items < clusters) ? p.n_items : clusters);
-  k_fantasy_tc2<D4, EW><<<grid, 128 + 32 * EW, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+  k_fantasy_tc2<D4, EW, REFINE><<<grid, 128 + 32 * EW, C::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
   SBO_LAUNCH_CHECK();
   return SBO_OK;
 }
@@ -867,7 +949,8 @@ static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
 }  // namespace tc
 
 // keys of the exact pruning (pairs.cu): sorted key_x[nx] (max side), key_z[nz] (min side), slot -> counts row
-struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run; };
+struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run;
+                          int refine; int2* amb_list; unsigned long long* amb_count; long long amb_cap; };
 // per tile of `tile` consecutive sorted entries: max (x side) or min (z side) of the keys
 __global__ void __launch_bounds__(256)
 k_tile_keys(long long n, int tile, int want_max, const double* __restrict__ key, double* __restrict__ out) {
@@ -936,16 +1019,24 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   const double* zn = aux_z; const double* mz = zn + (size_t)d * nz; const double* sz = mz + (size_t)nc * nz;
   float* rowrec = (float*)ctx->tc_row.p;
   float* colrec = (float*)ctx->tc_col.p;
+  // refinement band of the split mode: c1 = 2^-20 (operand split: representation + dropped lo.lo) + one ulp (2^-23) of the
+  // running sum per tensor-core accumulation step of the hi.hi segment (K/8 steps); the cross segments are accumulated
+  // first at 2^-11 of that size.  e_abs / d_mu / d_t: ex2.approx, FP32 records and the FP32 epilogue arithmetic.
+  const bool refine = pr && pr->refine && split;
+  const double c1 = refine ? (9.5367431640625e-07 + (fc.npad / 8) * 1.1920928955078125e-07) : 0.0;
+  const double esc = refine ? sqrt(c1) : 0.0;
+  tc::RefineArgs ra{};
+  if (refine) { ra.list = pr->amb_list; ra.count = pr->amb_count; ra.cap = pr->amb_cap; ra.e_abs = 2e-6f; ra.d_mu = 2e-6f; ra.d_t = 4e-6f; }
   ev_begin(ctx, 6);
   if (D4 == 1) {
-    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec);
+    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec, esc);
     SBO_LAUNCH_CHECK();
-    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec);
+    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec, esc);
     SBO_LAUNCH_CHECK();
   } else {
-    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec);
+    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec, esc);
     SBO_LAUNCH_CHECK();
-    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec);
+    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec, esc);
     SBO_LAUNCH_CHECK();
   }
   int* err = (int*)ctx->tc_err.p;
@@ -954,6 +1045,7 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   // outweighs the MMAs (short K) or carries 12-float records (d > 4)
   int variant = (int)ctx->opt_fantasy_variant;
   if (variant < 0) variant = 5 | ((fc.npad <= 256 || D4 == 2) ? 2 : 0);
+  if (refine) variant |= 5;        // the refining epilogue exists in the 2-CTA kernel only
   // tile geometry of the chosen kernel and the raster of its work items
   const bool two = (variant & 4) != 0;
   const int tile_x = two ? 2 * tc::BM : tc::BM, tile_z = (two || (variant & 1)) ? 256 : 128;
@@ -972,7 +1064,8 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   ev_end(ctx);            // record prep = phase 6
   ev_begin(ctx, 4);       // the GEMM kernel alone = phase 4 (closed by the caller)
 #define TC_LAUNCH(BN_, D4_, EW_) SBO_TRY((tc::launch<BN_, D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err, item_list, n_list, row_perm)))
-#define TC_LAUNCH2(D4_, EW_) SBO_TRY((tc::launch2<D4_, EW_>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err, item_list, n_list, row_perm, gx)))
+#define TC_LAUNCH2(D4_, EW_) do { if (refine) SBO_TRY((tc::launch2<D4_, EW_, true>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err, item_list, n_list, row_perm, gx, ra))); \
+                                 else SBO_TRY((tc::launch2<D4_, EW_, false>(ctx, fc, split, nx, nz, nxp, nzp, Vx, Vz, rowrec, colrec, counts_c, err, item_list, n_list, row_perm, gx, ra))); } while (0)
   if (variant & 4) {            // 2-CTA pairs (cta_group::2), BN = 256
     if (D4 == 1) { if (variant & 2) TC_LAUNCH2(1, 8); else TC_LAUNCH2(1, 4); }
     else         { if (variant & 2) TC_LAUNCH2(2, 8); else TC_LAUNCH2(2, 4); }

@@ -123,7 +123,14 @@ k_pairs_expander(PairConsts pc, long long nx, long long nz, const double* __rest
   const long long z0 = (long long)blockIdx.y * z_per_split;
   const long long z1 = min(nz, z0 + z_per_split);
   unsigned long long tiles = 0;
+  const long long o_hit = active ? (out_pos ? (long long)out_pos[t] : t) : 0;
+  int poll = 0;
   for (long long zb = z0; zb < z1; zb += PT) {
+    // the z range is split over blockIdx.y: a hit found by another split settles the constraint here as well (the flags
+    // are only ever set, so a stale read costs work, never correctness)
+    if (gridDim.y > 1 && active && (++poll & 3) == 0)
+      for (int c = 0; c < pc.nc; ++c)
+        if (!((found >> c) & 1u) && *(volatile const unsigned char*)(hits + (size_t)c * nx + o_hit)) found |= 1u << c;
     if (__syncthreads_and((found | dead) == full)) break;
     if (bb) {   // exact culling: skip the tile when no thread's x can reach its bounding box (see tile_lower_bound)
       bool need = false;
@@ -149,14 +156,16 @@ k_pairs_expander(PairConsts pc, long long nx, long long nz, const double* __rest
           s = __dadd_rn(s, __dmul_rn(df, df));
         }
         for (int c = 0; c < pc.nc; ++c)
-          if (!((found >> c) & 1u) && r2[c] >= 0.0 && reach_test(s, r2[c], u[c], pc.L[c])) found |= 1u << c;
+          if (!((found >> c) & 1u) && r2[c] >= 0.0 && reach_test(s, r2[c], u[c], pc.L[c])) {
+            found |= 1u << c;
+            if (gridDim.y > 1) hits[(size_t)c * nx + o_hit] = 1;       // publish at once: the other z splits stop looking
+          }
       }
     }
   }
   if (active) {
-    const long long o = out_pos ? out_pos[t] : t;      // hit flags go back in the caller's (gathered) candidate order
-    for (int c = 0; c < pc.nc; ++c)
-      if ((found >> c) & 1u) hits[(size_t)c * nx + o] = 1;
+    for (int c = 0; c < pc.nc; ++c)                    // hit flags go back in the caller's (gathered) candidate order
+      if ((found >> c) & 1u) hits[(size_t)c * nx + o_hit] = 1;
   }
   if (threadIdx.x == 0 && pair_counter) atomicAdd(pair_counter, tiles * (unsigned long long)PT * PT * pc.nc);
 }
@@ -186,7 +195,11 @@ k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restri
   const long long x0 = (long long)blockIdx.y * x_per_split;
   const long long x1 = min(nx, x0 + x_per_split);
   unsigned long long tiles = 0;
+  int poll = 0;
   for (long long xb = x0; xb < x1; xb += PT) {
+    if (gridDim.y > 1 && active && (++poll & 3) == 0)      // a hit found by another x split settles the constraint here too
+      for (int c = 0; c < pc.nc; ++c)
+        if (!((found >> c) & 1u) && *(volatile const unsigned char*)(hits + (size_t)c * nz + t)) found |= 1u << c;
     if (__syncthreads_and(found == full)) break;
     if (bb) {   // exact culling against the x tile's bounding box and its largest radius per constraint
       bool need = false;
@@ -221,7 +234,10 @@ k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restri
         }
         for (int c = 0; c < pc.nc; ++c) {
           const double r2 = rs[c][j];
-          if (!((found >> c) & 1u) && r2 >= 0.0 && reach_test(s, r2, us[c][j], pc.L[c])) found |= 1u << c;
+          if (!((found >> c) & 1u) && r2 >= 0.0 && reach_test(s, r2, us[c][j], pc.L[c])) {
+            found |= 1u << c;
+            if (gridDim.y > 1) hits[(size_t)c * nz + t] = 1;
+          }
         }
       }
     }
@@ -243,7 +259,10 @@ static int launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long lon
   if (bx == 0) return SBO_OK;
   long long splits = 1;
   const long long tiles = cdiv(ntile, PT);
-  while (bx * splits < 4 * 148 && splits * 8 <= tiles && splits < 65535) splits *= 2;   // enough CTAs, >= 8 tiles each
+  // many small work units: the cost of a CTA varies by orders of magnitude (points next to the safe-set boundary scan
+  // many tiles, far ones are culled at once), so a single wave of CTAs -- a sharded run has 1/nranks of the thread-side
+  // points -- leaves the GPU waiting for the slowest one.  The splits share hits through the global flags.
+  while (bx * splits < 16 * 148 && splits * 8 <= tiles && splits < 65535) splits *= 2;
   const long long per = cdiv(cdiv(ntile, splits), PT) * PT;
   dim3 grid((unsigned)bx, (unsigned)cdiv(ntile, per));
   // bounding boxes of the staged side's tiles for the exact culling (option pair_cull, default on)
@@ -861,10 +880,122 @@ k_fantasy_dmma(FantasyConsts fc, DmmaArgs a) {
 int fantasy_build_items(sbo_ctx* ctx, long long nx, long long nz, int tile_x, int tile_z, int gx, const double* key_x,
                         const double* key_z, const long long** item_list, long long* n_list);
 
-struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run; };
+struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run;
+                          int refine; int2* amb_list; unsigned long long* amb_count; long long amb_cap; };
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
                    long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c,
                    const FantasyPruneArgs* pr);
+
+
+// =============================================================================================
+// FP64 re-evaluation of the pairs the split-TF32 GEMM could not settle (fantasy_tc.cu epilogue_chunk_refine).
+//   1. mark the distinct candidate slots / z columns of the ambiguous list, compact them, build slot -> rank maps
+//   2. FP64 rows V = L^-1 K(X, .) for those points only (posterior kernels on explicit points)
+//   3. one warp per ambiguous pair: FP64 dot products + the FP64 epilogue of k_fantasy_f64; safe pairs are added to the
+//      candidate's count.  The GEMM counted only the pairs that are safe for EVERY covariance inside the error bound, so
+//      the total equals the FP64 count (up to pairs within FP64 rounding of the threshold).
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_amb_mark(long long n, const int2* __restrict__ list, uint32_t* __restrict__ xm, uint32_t* __restrict__ zm) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int2 e = list[t];
+  atomicOr(xm + (e.x >> 5), 1u << (e.x & 31));
+  atomicOr(zm + (e.y >> 5), 1u << (e.y & 31));
+}
+// rank[slot] = position in the compacted list; pts[r][d] = raw coordinates (xn * Xstd + Xmean)
+__global__ void __launch_bounds__(256) k_amb_points(ModelSpec ms, long long m, long long ntot, const long long* __restrict__ ids,
+                                                    const double* __restrict__ xn_soa, int* __restrict__ rank, double* __restrict__ pts) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const long long id = ids[r];
+  rank[id] = (int)r;
+  for (int k = 0; k < ms.d; ++k) pts[(size_t)r * ms.d + k] = xn_soa[(size_t)k * ntot + id] * ms.Xstd[k] + ms.Xmean[k];
+}
+template <int D>
+__global__ void __launch_bounds__(256)
+k_refine_pairs(FantasyConsts fc, long long n_amb, const int2* __restrict__ list, long long nx, long long nz, long long mx, long long mz_,
+               const int* __restrict__ rank_x, const int* __restrict__ rank_z, const double* __restrict__ Vx, const double* __restrict__ Vz,
+               const double* __restrict__ xn, const double* __restrict__ ax, const double* __restrict__ bx,
+               const double* __restrict__ zn, const double* __restrict__ mz, const double* __restrict__ sz,
+               int* __restrict__ counts, const int* __restrict__ row_perm, unsigned long long* __restrict__ n_safe) {
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= n_amb) return;
+  const int lane = threadIdx.x & 31;
+  const int2 e = list[w];
+  const long long xi = e.x, zi = e.y;
+  const long long rx = rank_x[xi], rz = rank_z[zi];
+  bool ok = true;
+  for (int c = 0; c < fc.nc && ok; ++c) {
+    const double* vx = Vx + ((size_t)c * mx + rx) * fc.npad;
+    const double* vz = Vz + ((size_t)c * mz_ + rz) * fc.npad;
+    double acc = 0.0;
+    for (int k = lane; k < fc.npad; k += 32) acc = fma(vx[k], vz[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) { const double df = zn[(size_t)k * nz + zi] - xn[(size_t)k * nx + xi]; s += df * df * fc.inv_ell[c][k]; }
+    const double cc = fc.sf2[c] * exp(-0.5 * s) - acc;
+    const double mu = mz[(size_t)c * nz + zi] + cc * ax[(size_t)c * nx + xi];
+    const double s2 = sz[(size_t)c * nz + zi] - cc * cc * bx[(size_t)c * nx + xi];
+    ok = (mu - fc.beta * sqrt(fmax(s2, 0.0))) >= 0.0;
+  }
+  if (ok && lane == 0) {
+    atomicAdd(counts + (row_perm ? row_perm[xi] : xi), 1);
+    atomicAdd(n_safe, 1ULL);
+  }
+}
+
+static int refine_ambiguous(sbo_ctx* ctx, const FantasyConsts& fc, long long nx, long long nz, int* counts, const int* row_perm) {
+  PairStage& ps = ctx->ps;
+  const ModelSpec& ms = ctx->ms;
+  const int d = fc.d, nc = fc.nc;
+  unsigned long long h[2] = {0, 0};
+  SBO_CUDA(cudaMemcpyAsync(h, ctx->amb_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  const long long n_amb = (long long)h[0];
+  const long long cap = (long long)(ctx->amb_list.cap / sizeof(int2));
+  ps.n_ambiguous = n_amb; ps.n_refined_safe = 0;
+  if (n_amb > cap)
+    return sbo_fail(ctx, SBO_ERR_NOMEM, "split-TF32 refinement: " + std::to_string(n_amb) + " ambiguous pairs exceed the list capacity " +
+                                            std::to_string(cap) + " (use precision fp64, or option fantasy_refine = 0)");
+  if (n_amb == 0) return SBO_OK;
+  const int2* list = (const int2*)ctx->amb_list.p;
+  const long long wx = cdiv(nx, 32), wz = cdiv(nz, 32);
+  SBO_TRY(sbo_ensure(ctx, ctx->amb_mask, sizeof(uint32_t) * (size_t)(wx + wz)));
+  SBO_CUDA(cudaMemsetAsync(ctx->amb_mask.p, 0, sizeof(uint32_t) * (size_t)(wx + wz), ctx->stream));
+  uint32_t* xm = (uint32_t*)ctx->amb_mask.p; uint32_t* zm = xm + wx;
+  k_amb_mark<<<(unsigned)cdiv(n_amb, 256), 256, 0, ctx->stream>>>(n_amb, list, xm, zm);
+  SBO_LAUNCH_CHECK();
+  long long mx = 0, mzd = 0;
+  SBO_TRY(compact_mask(ctx, xm, nx, ctx->amb_xd, &mx));
+  SBO_TRY(compact_mask(ctx, zm, nz, ctx->amb_zd, &mzd));
+  SBO_TRY(sbo_ensure(ctx, ctx->amb_rx, sizeof(int) * (size_t)nx));
+  SBO_TRY(sbo_ensure(ctx, ctx->amb_rz, sizeof(int) * (size_t)nz));
+  SBO_TRY(sbo_ensure(ctx, ctx->amb_pts, sizeof(double) * (size_t)(mx + mzd) * d));
+  SBO_TRY(sbo_ensure(ctx, ctx->amb_vx, sizeof(double) * (size_t)nc * mx * ms.npad));
+  SBO_TRY(sbo_ensure(ctx, ctx->amb_vz, sizeof(double) * (size_t)nc * mzd * ms.npad));
+  const double* xn = (const double*)ctx->aux_x.p; const double* ax = xn + (size_t)d * nx; const double* bx = ax + (size_t)nc * nx;
+  const double* zn = (const double*)ctx->aux_z.p; const double* mz = zn + (size_t)d * nz; const double* sz = mz + (size_t)nc * nz;
+  double* ptx = (double*)ctx->amb_pts.p; double* ptz = ptx + (size_t)mx * d;
+  k_amb_points<<<(unsigned)cdiv(mx, 256), 256, 0, ctx->stream>>>(ms, mx, nx, (const long long*)ctx->amb_xd.p, xn, (int*)ctx->amb_rx.p, ptx);
+  SBO_LAUNCH_CHECK();
+  k_amb_points<<<(unsigned)cdiv(mzd, 256), 256, 0, ctx->stream>>>(ms, mzd, nz, (const long long*)ctx->amb_zd.p, zn, (int*)ctx->amb_rz.p, ptz);
+  SBO_LAUNCH_CHECK();
+  SBO_TRY(posterior_vrows_dev(ctx, mx, ptx, (double*)ctx->amb_vx.p));
+  SBO_TRY(posterior_vrows_dev(ctx, mzd, ptz, (double*)ctx->amb_vz.p));
+  unsigned long long* nsafe = (unsigned long long*)ctx->amb_ctr.p + 1;
+#define RP(DD) k_refine_pairs<DD><<<(unsigned)cdiv(n_amb, 8), 256, 0, ctx->stream>>>(fc, n_amb, list, nx, nz, mx, mzd, (const int*)ctx->amb_rx.p, \
+      (const int*)ctx->amb_rz.p, (const double*)ctx->amb_vx.p, (const double*)ctx->amb_vz.p, xn, ax, bx, zn, mz, sz, counts, row_perm, nsafe)
+  switch (d) { case 1: RP(1); break; case 2: RP(2); break; case 3: RP(3); break; case 4: RP(4); break;
+               case 5: RP(5); break; case 6: RP(6); break; case 7: RP(7); break; default: RP(8); break; }
+#undef RP
+  SBO_LAUNCH_CHECK();
+  SBO_CUDA(cudaMemcpyAsync(h, ctx->amb_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+  ps.n_refined_safe = (long long)h[1];
+  return SBO_OK;
+}
 
 // =============================================================================================
 // staged host driver
@@ -894,7 +1025,7 @@ int pairs_prepare(sbo_ctx* ctx, int mode, int precision, double beta, const doub
     SBO_REQUIRE(ctx->keep_v == (precision == SBO_PREC_FP64 ? 1 : (precision == SBO_PREC_TF32 ? 2 : 3)),
                 "fantasy expander: run sbo_posterior with keep_v = 1 (FP64), 2 (TF32) or 3 (TF32x3) first");
   }
-  ev_reset(ctx, 4); ev_reset(ctx, 6);
+  ev_reset(ctx, 4); ev_reset(ctx, 6); ev_reset(ctx, 7);
   ev_begin(ctx, 6);
   long long nx = 0, nz = 0;
   ps.nz_full = 0;
@@ -1180,10 +1311,26 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
       ps.count_scale = nc;
     } else {   // record prep is logged as phase 6, the GEMM kernel as phase 4 (begun inside)
       long long run_pairs = nx * nz;
-      FantasyPruneArgs pr{key_x, key_z, row_perm, &run_pairs};
+      FantasyPruneArgs pr{key_x, key_z, row_perm, &run_pairs, 0, nullptr, nullptr, 0};
+      const bool refine = ps.precision == SBO_PREC_TF32X3 && ctx->opt_fantasy_refine;
+      if (refine) {
+        // list capacity: a 256th of the pairs, between 1 M and 32 M entries (C4: ~1 M ambiguous pairs of 3e10)
+        long long cap = nx * nz / 256;
+        cap = cap < (1LL << 20) ? (1LL << 20) : (cap > (1LL << 25) ? (1LL << 25) : cap);
+        SBO_TRY(sbo_ensure(ctx, ctx->amb_list, sizeof(int2) * (size_t)cap));
+        SBO_TRY(sbo_ensure(ctx, ctx->amb_ctr, 2 * sizeof(unsigned long long)));
+        SBO_CUDA(cudaMemsetAsync(ctx->amb_ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        pr.refine = 1; pr.amb_list = (int2*)ctx->amb_list.p; pr.amb_count = (unsigned long long*)ctx->amb_ctr.p;
+        pr.amb_cap = (long long)(ctx->amb_list.cap / sizeof(int2));
+      }
       SBO_TRY(fantasy_tc_run(ctx, fc, ps.precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p,
                              (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt, &pr));
       ps.pairs_evaluated = (ps.sorted ? run_pairs : nx * nz) * nc;
+      if (refine) {
+        ev_end(ctx);
+        ev_begin(ctx, 7);
+        SBO_TRY(refine_ambiguous(ctx, fc, nx, nz, cnt, row_perm));
+      }
     }
     ev_end(ctx);
   }
@@ -1242,6 +1389,7 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
   SBO_CUDA(cudaStreamSynchronize(ctx->stream));
   ev_collect(ctx);
   out->n_hit = (int64_t)h[1];
+  out->n_ambiguous = ps.n_ambiguous; out->n_refined_safe = ps.n_refined_safe;
   if (ps.counted) out->pairs_evaluated = (int64_t)h[0] * ps.count_scale;
   else out->pairs_evaluated = ps.pairs_evaluated;
   if (out->pairs_evaluated > out->pairs_algorithmic) out->pairs_evaluated = out->pairs_algorithmic;

@@ -744,6 +744,28 @@ int posterior_points(sbo_ctx* ctx, int64_t m, const double* x, double* mean, dou
   return SBO_OK;
 }
 
+// FP64 rows V_i = L_i^-1 K_i(X, p) of m explicit points already on the device (raw coordinates, [m][d] row-major), for
+// the constraints: vout[(G-1)][m][npad].  Used by the FP64 re-evaluation of the split-TF32 fantasy expander.
+int posterior_vrows_dev(sbo_ctx* ctx, long long m, const double* pts_dev, double* vout) {
+  SBO_REQUIRE(ctx->have_model && m >= 1 && pts_dev && vout, "posterior_vrows_dev: bad arguments");
+  const ModelSpec& ms = ctx->ms;
+  GridSpec tmp{};
+  tmp.kind = 2; tmp.d = ms.d; tmp.N = m; tmp.first = 0; tmp.count = m;
+  tmp.explicit_pts = pts_dev;
+  SBO_TRY(sbo_ensure(ctx, ctx->pp_m, sizeof(double) * (size_t)ms.G * m));
+  SBO_TRY(sbo_ensure(ctx, ctx->pp_v, sizeof(double) * (size_t)ms.G * m));
+  const long long P = chunk_points(ctx, ms, m);
+  SBO_TRY(sbo_ensure(ctx, ctx->pp_k, sizeof(double) * (size_t)ms.G * ms.npad * P));
+  const int64_t keep_variant = ctx->opt_posterior_variant;
+  for (long long p0 = 0; p0 < m; p0 += P) {
+    const int valid = (int)((m - p0) < P ? (m - p0) : P);
+    SBO_TRY(crosscov_dispatch(ctx, tmp, p0, (int)P, valid, (double*)ctx->pp_k.p, (double*)ctx->pp_m.p, m, nullptr, nullptr, -1));
+    SBO_TRY(solve_dispatch(ctx, (const double*)ctx->pp_k.p, (int)P, p0, valid, (double*)ctx->pp_v.p, m, 1, vout, m));
+  }
+  (void)keep_variant;
+  return SBO_OK;
+}
+
 int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad) {
   GridSpec tmp;
   DevBuf &xbuf = ctx->pp_x, &gbuf = ctx->pp_g, &kbuf = ctx->pp_k;

@@ -82,6 +82,10 @@ class GridEngine:
     def kernel_launches(self, reset=False):
         return int(self._lib.sbo_kernel_launches(self._h, 1 if reset else 0))
 
+    def mem_peak(self, reset=False):
+        """High-water mark (bytes) of the device memory of the context's work buffers."""
+        return int(self._lib.sbo_mem_peak(self._h, 1 if reset else 0))
+
     def phase_ms(self):
         out = {}
         v = C.c_double()
@@ -266,7 +270,8 @@ class GridEngine:
         return {"best_idx": r.best_idx, "best_value": r.best_value,
                 "per_idx": [r.per_idx[c] for c in range(nc)], "per_value": [r.per_value[c] for c in range(nc)],
                 "n_x": r.n_x, "n_z": r.n_z, "pairs_algorithmic": r.pairs_algorithmic,
-                "pairs_evaluated": r.pairs_evaluated, "n_hit": r.n_hit}
+                "pairs_evaluated": r.pairs_evaluated, "n_hit": r.n_hit, "n_ambiguous": r.n_ambiguous,
+                "n_refined_safe": r.n_refined_safe}
 
     def expander(self, beta, L=None, mode=capi.MODE_LIPSCHITZ, precision=capi.PREC_FP64, want_counts=False):
         r = capi.PairResult()

@@ -227,14 +227,15 @@ def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
     red = reduce_arg([(loc["per_value"][c], loc["per_idx"][c]) for c in range(nmask)], device, not goose, group) if nmask else []
     per_value, per_idx = [v for v, _ in red], [i for _, i in red]
     bi, bv = first_best(per_value, per_idx, maximize=not goose)
-    tot = gather_scalars([nz, loc["n_hit"], loc["pairs_evaluated"]], device, group).sum(axis=0)
+    tot = gather_scalars([nz, loc["n_hit"], loc["pairs_evaluated"], loc.get("n_ambiguous", 0), loc.get("n_refined_safe", 0)],
+                         device, group).sum(axis=0)
     if big and hasattr(eng, "release"):
         eng.release(2)                       # gathered operands: the next step's V rows need the room
     tr.mark("finish")
     tr.dump()
     out = {"best_idx": bi, "best_value": bv, "per_idx": per_idx, "per_value": per_value, "n_x": n_total,
            "n_z": int(tot[0]), "n_hit": int(tot[1]), "pairs_evaluated": int(tot[2]),
-           "pairs_algorithmic": n_total * int(tot[0]) * nc, "local": loc}
+           "pairs_algorithmic": n_total * int(tot[0]) * nc, "n_ambiguous": int(tot[3]), "n_refined_safe": int(tot[4]), "local": loc}
     return out
 
 

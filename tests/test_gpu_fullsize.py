@@ -8,7 +8,8 @@
   (SURVEY.md section 7 step 1): x is an expander for constraint c iff dist(x, Z) <= ucb_c(x)/L.
 
 Stated tolerances (normalised margin m = min_c (mu'_c - beta sigma'_c), sf2 = 1 on these models):
-  tf32x3  a pair decision may differ from FP64 only where |m| <= 1e-4 * sf2              (north_star's TF32-mode tolerance)
+  tf32x3  split TF32 + FP64 refinement of every pair inside the FP32 error bound (default): the FP64 counts, exactly;
+          with option fantasy_refine = 0 a decision may differ only where |m| <= 1e-4 * sf2 (north_star's TF32 tolerance)
   tf32    single pass: only where |m| <= 1e-3 * sf2 * (1 + gain(x))  (operand rounding 2^-11, amplified by the update gain)
   fp64    GPU FP64 kernel: only where |m| <= 1e-4 * sf2 (expected: identical)
 """
@@ -47,24 +48,29 @@ def test_c4_fantasy_counts_vs_full_size_oracle(engine):
     engine.set_grid(lo, hi, pts)
     xi = f["x_idx"]
     counts = {}
-    for prec in ("tf32x3", "tf32", "fp64"):
-        p, kv = capi.PRECISIONS[prec]
+    for prec in ("tf32x3", "tf32x3-norefine", "tf32", "fp64"):
+        p, kv = capi.PRECISIONS[prec.split("-")[0]]
+        engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 1)
         engine.posterior(keep_v=kv, fetch=False)
         s = engine.sets(beta, capi.UNSAFE_ALL)
         assert s["n_safe"] == int(f["n_safe"]) and s["n_unsafe"] == int(f["n_unsafe"])
         ex = engine.expander(beta, None, capi.MODE_FANTASY, p, want_counts=True)
+        engine.set_option("fantasy_refine", 1)
         counts[prec] = ex["counts"].astype(np.int64)
-        print(f"C4 {prec}: n_hit {ex['n_hit']}, pairs evaluated {ex['pairs_evaluated']} of {ex['pairs_algorithmic']}, best {ex['best_idx']}")
-        _check(f"C4 {prec}", counts[prec][xi], f["counts"], f["near_tf32"] if prec == "tf32" else f["near_1e4"])
+        print(f"C4 {prec}: n_hit {ex['n_hit']}, pairs evaluated {ex['pairs_evaluated']} of {ex['pairs_algorithmic']}, best {ex['best_idx']}, "
+              f"refined {ex['n_ambiguous']} pairs ({ex['n_refined_safe']} safe)")
+        near = f["near_tf32"] if prec == "tf32" else (np.zeros_like(f["near_1e4"]) if prec in ("tf32x3", "fp64") else f["near_1e4"])
+        _check(f"C4 {prec}", counts[prec][xi], f["counts"], near)
         engine.release(3)
     # all 116 645 candidates: the split-TF32 mode against the GPU FP64 kernel (itself pinned to the oracle above)
     d = np.abs(counts["tf32x3"] - counts["fp64"])
     print(f"C4 tf32x3 vs fp64 over all candidates: {int((d > 0).sum())} candidates differ, sum|diff| = {int(d.sum())} of "
           f"{int(counts['fp64'].sum())} newly-safe pairs; expander set sizes {int((counts['tf32x3'] > 0).sum())} / {int((counts['fp64'] > 0).sum())}")
-    # the FP32 accumulator of the tensor core bounds the split mode (error grows with K): over all candidates its
-    # differing decisions stay a small fraction of the newly-safe pairs and the expander SET differs by a few candidates
-    assert d.sum() <= 5e-4 * counts["fp64"].sum() + 8
-    assert abs(int((counts["tf32x3"] > 0).sum()) - int((counts["fp64"] > 0).sum())) <= 1e-3 * (counts["fp64"] > 0).sum() + 2
+    assert d.sum() <= 2, "the refined split-TF32 counts must be the FP64 counts"
+    dn = np.abs(counts["tf32x3-norefine"] - counts["fp64"])
+    print(f"C4 tf32x3 without the refinement vs fp64: {int((dn > 0).sum())} candidates differ, sum|diff| = {int(dn.sum())}")
+    # unrefined, the FP32 accumulator of the tensor core bounds the split mode (error grows with K)
+    assert dn.sum() <= 5e-4 * counts["fp64"].sum() + 8
     d1 = np.abs(counts["tf32"] - counts["fp64"])
     print(f"C4 tf32 (single pass) vs fp64: {int((d1 > 0).sum())} candidates differ, sum|diff| = {int(d1.sum())}")
 
@@ -80,15 +86,19 @@ def test_c5_model_fantasy_counts_on_sampled_points(engine):
     engine.set_model(ds)
     engine.set_points(P)
     xl = f["x_local"]
-    for prec in ("tf32x3", "tf32", "fp64"):
-        p, kv = capi.PRECISIONS[prec]
+    for prec in ("tf32x3", "tf32x3-norefine", "tf32", "fp64"):
+        p, kv = capi.PRECISIONS[prec.split("-")[0]]
+        engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 1)
         engine.posterior(keep_v=kv, fetch=False)
         s = engine.sets(beta, capi.UNSAFE_ALL)
         assert s["n_safe"] == int(f["n_safe"]) and s["n_unsafe"] == int(f["n_unsafe"])
         ex = engine.expander(beta, None, capi.MODE_FANTASY, p, want_counts=True)
-        print(f"C5 model {prec}: n_hit {ex['n_hit']}, pairs evaluated {ex['pairs_evaluated']} of {ex['pairs_algorithmic']}")
+        engine.set_option("fantasy_refine", 1)
+        print(f"C5 model {prec}: n_hit {ex['n_hit']}, pairs evaluated {ex['pairs_evaluated']} of {ex['pairs_algorithmic']}, "
+              f"refined {ex['n_ambiguous']} pairs ({ex['n_refined_safe']} safe)")
         assert (ex["counts"][np.setdiff1d(np.arange(P.shape[0]), xl)] == 0).all()
-        _check(f"C5 model {prec}", ex["counts"][xl], f["counts"], f["near_tf32"] if prec == "tf32" else f["near_1e4"])
+        near = f["near_tf32"] if prec == "tf32" else (np.zeros_like(f["near_1e4"]) if prec in ("tf32x3", "fp64") else f["near_1e4"])
+        _check(f"C5 model {prec}", ex["counts"][xl], f["counts"], near)
         engine.release(3)
 
 

@@ -557,10 +557,18 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
         assert np.all(d2 <= amb), (int(d2.max()), int(amb.max()), int((d2 > amb).sum()))
         out.update(diff_vs_tf32_oracle=int(d1.sum()), diff_vs_fp64=int(d2.sum()), ambiguous=int(amb.sum()))
     else:
-        amb = (margin <= IMPL_TOL * scale).sum(axis=0)
+        # split-TF32 + FP64 refinement of every pair inside the FP32 error bound (option fantasy_refine, default on): the
+        # counts are the FP64 counts; only a pair within FP64 rounding of the threshold may differ
+        exact = (margin <= 1e-12 * scale).sum(axis=0)
         d2 = np.abs(got - w64)
-        assert np.all(d2 <= amb), (int(d2.max()), int(amb.max()), int((d2 > amb).sum()))
-        out.update(diff_vs_fp64=int(d2.sum()), ambiguous=int(amb.sum()))
+        assert np.all(d2 <= exact), (int(d2.max()), int(exact.max()), int((d2 > exact).sum()))
+        assert ex["n_ambiguous"] >= ex["n_refined_safe"] >= 0
+        # without the refinement the FP32 pipeline decides: differences only near the threshold
+        amb = (margin <= IMPL_TOL * scale).sum(axis=0)
+        d3 = np.abs(ex_all["counts"][S].astype(np.int64) - w64)       # ex_all: un-pruned, refined as well
+        assert np.all(d3 <= exact)
+        out.update(diff_vs_fp64=int(d2.sum()), ambiguous_band=int(amb.sum()), refined=int(ex["n_ambiguous"]),
+                   refined_safe=int(ex["n_refined_safe"]))
     return out
 
 
