@@ -41,8 +41,10 @@ def parse():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--mode", default=os.environ.get("SBO_BENCH_MODE", "fantasy"))
-    ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "tf32x3"),
-                    help="fantasy GEMM operands: tf32x3 (default: split TF32, FP32-class accuracy, meets the 1e-4 tolerance), tf32 (single pass), fp64")
+    ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "tf32"),
+                    help="fantasy GEMM operands: tf32 (default: single TF32 pass; every pair inside its error bound is re-evaluated in FP64, "
+                         "so the counts are the FP64 counts), tf32x3 (split TF32, same refinement with a 100x narrower band), fp64 (DMMA)")
+    ap.add_argument("--refine", type=int, default=2, help="FP64 refinement of the tensor-core modes: 2 (library default) tf32 and tf32x3, 1 tf32x3 only, 0 off")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end repetitions (default max(2, steps); the first is dropped when > 1)")
     ap.add_argument("--orchestrator", default="library", choices=["library", "torch"],
                     help="multi-GPU: collectives inside libsbo_b200 (sbo_comm_init, default) or issued by sharded.py through torch.distributed")
@@ -281,10 +283,13 @@ def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
     from sbo_b200 import workloads, sharded
     ds5, lo5, hi5, pts5, beta5 = workloads.c5()
     n5, d5 = ds5["X_norm"].shape
-    out = {"workload": "C5: synthetic step, d=6, N=16^6=2^24 grid, n=2048, G=4 (3 constraints)", "precision": "tf32", "n_gpus": world}
+    out = {"workload": "C5: synthetic step, d=6, N=16^6=2^24 grid, n=2048, G=4 (3 constraints)", "precision": "tf32", "refine": 0, "n_gpus": world}
     try:
         eng.release(3)
         torch.cuda.empty_cache()
+        # tensor-core decisions at this size: the TF32 band holds ~3e8 pairs per rank here and their FP64 re-evaluation at
+        # n = 2048 would gather ~30 TB of rows per rank (the refinement list is bounded at 32 M pairs)
+        eng.set_option("fantasy_refine", 0)
         eng.set_grid(lo5, hi5, pts5)
         if world > 1:
             eng.set_shard_cyclic(rank, world, 256)
@@ -357,6 +362,7 @@ def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
         torch.cuda.empty_cache()
     except Exception as e:  # pragma: no cover
         out["error"] = repr(e)[:400]
+    eng.set_option("fantasy_refine", int(args.refine))
     return out
 
 
@@ -390,6 +396,7 @@ def run_ours(args):
                 _shc.init_comm(eng, dev)
     fantasy = args.mode == "fantasy"
     eng.set_option("fantasy_prune", int(args.prune))
+    eng.set_option("fantasy_refine", int(args.refine))
 
     def step(upload=True):
         """One acquisition step on this rank's shard.  Multi-GPU: collectives between the stages, issued on the
@@ -505,6 +512,7 @@ def run_ours(args):
         flops = evaluated / world * (2.0 * n + 3 * d + 20)      # rank 0's share (z is sharded evenly)
         t_k = ph["pairs"] * 1e-3
         passes = 3 if args.precision == "tf32x3" else 1
+        t_k += ph.get("refine", 0.0) * 1e-3 * 0     # the FP64 refinement is its own phase (phase_ms.refine), not part of the GEMM
         if args.precision == "fp64":
             peak, src = peaks.get("fp64_tflops"), "cuBLAS FP64 GEMM measured in this run"
         elif mp.get("bf16_tflops_sustained"):
@@ -536,7 +544,7 @@ def run_ours(args):
             "config": {"workload": wl_name, "mode": args.mode, "precision": args.precision, "N": N, "n": n, "d": d, "G": G,
                        "beta": beta, "n_safe": int(res["n_safe"]), "n_unsafe": int(res["n_unsafe"]), "n_min": int(res["n_min"]),
                        "pairs": pairs, "pairs_evaluated": int(ex["pairs_evaluated"]), "n_hit": int(ex["n_hit"]), "x_new_idx": int(res["x_new_idx"]),
-                       "prune": int(args.prune), "refined_pairs_fp64": int(ex.get("n_ambiguous", 0)), "refined_safe": int(ex.get("n_refined_safe", 0)),
+                       "prune": int(args.prune), "refine": int(args.refine), "refined_pairs_fp64": int(ex.get("n_ambiguous", 0)), "refined_safe": int(ex.get("n_refined_safe", 0)),
                        "value_counts": "all |S|*|Z|*(G-1) pairs: the exact pruning decides the skipped ones without evaluating them",
                        "l2": "256 MiB flush buffer written between timed steps; working set >> L2",
                        "excludes": "plant evaluation and hyper-parameter fit (host side in the reference too)"},

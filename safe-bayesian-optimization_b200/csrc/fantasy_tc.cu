@@ -239,20 +239,27 @@ __device__ __forceinline__ void epilogue_chunk_refine(const uint32_t (&acc)[32],
     const uint64_t cov = fma2(a2, minus1, ex);
     const uint64_t E = fma2(rc.ex, p[4 * D4 + 3], e_abs2);                // ex*ez + e_abs
     const uint64_t cl = fma2(E, minus1, cov), ch = add2(cov, E);
-    const uint64_t m_opt = add2(p[4 * D4 + 1], d_mu2), m_pes = fma2(d_mu2, minus1, p[4 * D4 + 1]);   // m_z +- d_mu
-    const uint64_t s_opt = fma2(d_t2, minus1, p[4 * D4 + 2]), s_pes = add2(p[4 * D4 + 2], d_t2);     // s'_z -+ d_t
+    const uint64_t m_opt = add2(p[4 * D4 + 1], d_mu2);                    // m_z + d_mu
+    const uint64_t s_opt = fma2(d_t2, minus1, p[4 * D4 + 2]);             // s'_z - d_t
     const uint64_t cl2 = mul2(cl, cl), ch2 = mul2(ch, ch);
-    const uint64_t mu_lo = fma2(cl, rc.ax, m_opt), mu_hi = fma2(ch, rc.ax, m_opt), mu_sf = fma2(cl, rc.ax, m_pes);
-    const uint64_t t_lo = fma2(cl2, rc.nbx, s_opt), t_hi = fma2(ch2, rc.nbx, s_opt), t_sf = fma2(cl2, rc.nbx, s_pes);
-    const uint64_t mm_lo = mul2(mu_lo, mu_lo), mm_hi = mul2(mu_hi, mu_hi), mm_sf = mul2(mu_sf, mu_sf);
+    const uint64_t mu_lo = fma2(cl, rc.ax, m_opt), mu_hi = fma2(ch, rc.ax, m_opt);
+    const uint64_t t_lo = fma2(cl2, rc.nbx, s_opt), t_hi = fma2(ch2, rc.nbx, s_opt);
+    const uint64_t mm_lo = mul2(mu_lo, mu_lo), mm_hi = mul2(mu_hi, mu_hi);
     float a0, a1, b0, b1, c0, c1, l0, l1;
+    const uint32_t pairbits = 3u << (2 * jp);
     upk2(mu_lo, a0, a1); upk2(t_lo, b0, b1); upk2(mm_lo, c0, c1);
     set_bit_if_safe(wlo, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wlo, a1, c1, b1, 2u << (2 * jp));
     upk2(mu_hi, a0, a1); upk2(t_hi, b0, b1); upk2(mm_hi, c0, c1);
     set_bit_if_safe(whi, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(whi, a1, c1, b1, 2u << (2 * jp));
-    upk2(mu_sf, a0, a1); upk2(t_sf, b0, b1); upk2(mm_sf, c0, c1); upk2(cl, l0, l1);
-    a0 = l0 < 0.f ? l0 : a0; a1 = l1 < 0.f ? l1 : a1;                     // lo < 0: not on the monotone branch -> never "settled safe"
-    set_bit_if_safe(wsf, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wsf, a1, c1, b1, 2u << (2 * jp));
+    // the pessimistic evaluation only matters for pairs that are not already settled unsafe: almost none are, so the
+    // whole warp usually skips it (warp-uniform branch)
+    if (__any_sync(0xffffffffu, ((wlo | whi) & pairbits) != 0u)) {
+      const uint64_t m_pes = fma2(d_mu2, minus1, p[4 * D4 + 1]), s_pes = add2(p[4 * D4 + 2], d_t2);   // m_z - d_mu, s'_z + d_t
+      const uint64_t mu_sf = fma2(cl, rc.ax, m_pes), t_sf = fma2(cl2, rc.nbx, s_pes), mm_sf = mul2(mu_sf, mu_sf);
+      upk2(mu_sf, a0, a1); upk2(t_sf, b0, b1); upk2(mm_sf, c0, c1); upk2(cl, l0, l1);
+      a0 = l0 < 0.f ? l0 : a0; a1 = l1 < 0.f ? l1 : a1;                   // lo < 0: not on the monotone branch -> never "settled safe"
+      set_bit_if_safe(wsf, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wsf, a1, c1, b1, 2u << (2 * jp));
+    }
   }
   S = wsf;
   U = ~wlo & ~whi;
@@ -1022,8 +1029,9 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   // refinement band of the split mode: c1 = 2^-20 (operand split: representation + dropped lo.lo) + one ulp (2^-23) of the
   // running sum per tensor-core accumulation step of the hi.hi segment (K/8 steps); the cross segments are accumulated
   // first at 2^-11 of that size.  e_abs / d_mu / d_t: ex2.approx, FP32 records and the FP32 epilogue arithmetic.
-  const bool refine = pr && pr->refine && split;
-  const double c1 = refine ? (9.5367431640625e-07 + (fc.npad / 8) * 1.1920928955078125e-07) : 0.0;
+  // Single-pass TF32 (option fantasy_refine = 2): the operand rounding itself, 2^-11 per operand -> 2^-10 (+2^-22) per product.
+  const bool refine = pr && pr->refine;
+  const double c1 = refine ? ((split ? 9.5367431640625e-07 : 9.7680091857910156e-04) + (fc.npad / 8) * 1.1920928955078125e-07) : 0.0;
   const double esc = refine ? sqrt(c1) : 0.0;
   tc::RefineArgs ra{};
   if (refine) { ra.list = pr->amb_list; ra.count = pr->amb_count; ra.cap = pr->amb_cap; ra.e_abs = 2e-6f; ra.d_mu = 2e-6f; ra.d_t = 4e-6f; }
@@ -1045,7 +1053,7 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   // outweighs the MMAs (short K) or carries 12-float records (d > 4)
   int variant = (int)ctx->opt_fantasy_variant;
   if (variant < 0) variant = 5 | ((fc.npad <= 256 || D4 == 2) ? 2 : 0);
-  if (refine) variant |= 5;        // the refining epilogue exists in the 2-CTA kernel only
+  if (refine) variant |= 7;        // the refining epilogue exists in the 2-CTA kernel only; it is heavier: 8 epilogue warps
   // tile geometry of the chosen kernel and the raster of its work items
   const bool two = (variant & 4) != 0;
   const int tile_x = two ? 2 * tc::BM : tc::BM, tile_z = (two || (variant & 1)) ? 256 : 128;

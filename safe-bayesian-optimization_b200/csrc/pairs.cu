@@ -1312,7 +1312,7 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     } else {   // record prep is logged as phase 6, the GEMM kernel as phase 4 (begun inside)
       long long run_pairs = nx * nz;
       FantasyPruneArgs pr{key_x, key_z, row_perm, &run_pairs, 0, nullptr, nullptr, 0};
-      const bool refine = ps.precision == SBO_PREC_TF32X3 && ctx->opt_fantasy_refine;
+      const bool refine = (ps.precision == SBO_PREC_TF32X3 && ctx->opt_fantasy_refine >= 1) || (ps.precision == SBO_PREC_TF32 && ctx->opt_fantasy_refine >= 2);
       if (refine) {
         // list capacity: a 256th of the pairs, between 1 M and 32 M entries (C4: ~1 M ambiguous pairs of 3e10)
         long long cap = nx * nz / 256;

@@ -8,9 +8,10 @@
   (SURVEY.md section 7 step 1): x is an expander for constraint c iff dist(x, Z) <= ucb_c(x)/L.
 
 Stated tolerances (normalised margin m = min_c (mu'_c - beta sigma'_c), sf2 = 1 on these models):
-  tf32x3  split TF32 + FP64 refinement of every pair inside the FP32 error bound (default): the FP64 counts, exactly;
-          with option fantasy_refine = 0 a decision may differ only where |m| <= 1e-4 * sf2 (north_star's TF32 tolerance)
-  tf32    single pass: only where |m| <= 1e-3 * sf2 * (1 + gain(x))  (operand rounding 2^-11, amplified by the update gain)
+  tf32, tf32x3   (default: FP64 refinement of every pair inside the tensor-core error bound) the FP64 counts, exactly
+  -norefine      option fantasy_refine = 0, the tensor-core value decides:
+                 tf32x3  a decision may differ only where |m| <= 1e-4 * sf2 (north_star's TF32-mode tolerance)
+                 tf32    only where |m| <= 1e-3 * sf2 * (1 + gain(x))  (operand rounding 2^-11, amplified by the update gain)
   fp64    GPU FP64 kernel: only where |m| <= 1e-4 * sf2 (expected: identical)
 """
 import importlib.util
@@ -48,18 +49,18 @@ def test_c4_fantasy_counts_vs_full_size_oracle(engine):
     engine.set_grid(lo, hi, pts)
     xi = f["x_idx"]
     counts = {}
-    for prec in ("tf32x3", "tf32x3-norefine", "tf32", "fp64"):
+    for prec in ("tf32", "tf32-norefine", "tf32x3", "tf32x3-norefine", "fp64"):
         p, kv = capi.PRECISIONS[prec.split("-")[0]]
         engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 1)
         engine.posterior(keep_v=kv, fetch=False)
         s = engine.sets(beta, capi.UNSAFE_ALL)
         assert s["n_safe"] == int(f["n_safe"]) and s["n_unsafe"] == int(f["n_unsafe"])
         ex = engine.expander(beta, None, capi.MODE_FANTASY, p, want_counts=True)
-        engine.set_option("fantasy_refine", 1)
+        engine.set_option("fantasy_refine", 2)
         counts[prec] = ex["counts"].astype(np.int64)
         print(f"C4 {prec}: n_hit {ex['n_hit']}, pairs evaluated {ex['pairs_evaluated']} of {ex['pairs_algorithmic']}, best {ex['best_idx']}, "
               f"refined {ex['n_ambiguous']} pairs ({ex['n_refined_safe']} safe)")
-        near = f["near_tf32"] if prec == "tf32" else (np.zeros_like(f["near_1e4"]) if prec in ("tf32x3", "fp64") else f["near_1e4"])
+        near = {"tf32-norefine": f["near_tf32"], "tf32x3-norefine": f["near_1e4"]}.get(prec, np.zeros_like(f["near_1e4"]))
         _check(f"C4 {prec}", counts[prec][xi], f["counts"], near)
         engine.release(3)
     # all 116 645 candidates: the split-TF32 mode against the GPU FP64 kernel (itself pinned to the oracle above)
@@ -67,12 +68,15 @@ def test_c4_fantasy_counts_vs_full_size_oracle(engine):
     print(f"C4 tf32x3 vs fp64 over all candidates: {int((d > 0).sum())} candidates differ, sum|diff| = {int(d.sum())} of "
           f"{int(counts['fp64'].sum())} newly-safe pairs; expander set sizes {int((counts['tf32x3'] > 0).sum())} / {int((counts['fp64'] > 0).sum())}")
     assert d.sum() <= 2, "the refined split-TF32 counts must be the FP64 counts"
+    dt = np.abs(counts["tf32"] - counts["fp64"])
+    print(f"C4 tf32 (refined, the bench default) vs fp64 over all candidates: {int((dt > 0).sum())} candidates differ, sum|diff| = {int(dt.sum())}")
+    assert dt.sum() <= 2, "the refined single-pass TF32 counts must be the FP64 counts"
     dn = np.abs(counts["tf32x3-norefine"] - counts["fp64"])
     print(f"C4 tf32x3 without the refinement vs fp64: {int((dn > 0).sum())} candidates differ, sum|diff| = {int(dn.sum())}")
     # unrefined, the FP32 accumulator of the tensor core bounds the split mode (error grows with K)
     assert dn.sum() <= 5e-4 * counts["fp64"].sum() + 8
-    d1 = np.abs(counts["tf32"] - counts["fp64"])
-    print(f"C4 tf32 (single pass) vs fp64: {int((d1 > 0).sum())} candidates differ, sum|diff| = {int(d1.sum())}")
+    d1 = np.abs(counts["tf32-norefine"] - counts["fp64"])
+    print(f"C4 tf32 (single pass, no refinement) vs fp64: {int((d1 > 0).sum())} candidates differ, sum|diff| = {int(d1.sum())}")
 
 
 def test_c5_model_fantasy_counts_on_sampled_points(engine):
@@ -86,18 +90,18 @@ def test_c5_model_fantasy_counts_on_sampled_points(engine):
     engine.set_model(ds)
     engine.set_points(P)
     xl = f["x_local"]
-    for prec in ("tf32x3", "tf32x3-norefine", "tf32", "fp64"):
+    for prec in ("tf32", "tf32-norefine", "tf32x3", "tf32x3-norefine", "fp64"):
         p, kv = capi.PRECISIONS[prec.split("-")[0]]
         engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 1)
         engine.posterior(keep_v=kv, fetch=False)
         s = engine.sets(beta, capi.UNSAFE_ALL)
         assert s["n_safe"] == int(f["n_safe"]) and s["n_unsafe"] == int(f["n_unsafe"])
         ex = engine.expander(beta, None, capi.MODE_FANTASY, p, want_counts=True)
-        engine.set_option("fantasy_refine", 1)
+        engine.set_option("fantasy_refine", 2)
         print(f"C5 model {prec}: n_hit {ex['n_hit']}, pairs evaluated {ex['pairs_evaluated']} of {ex['pairs_algorithmic']}, "
               f"refined {ex['n_ambiguous']} pairs ({ex['n_refined_safe']} safe)")
         assert (ex["counts"][np.setdiff1d(np.arange(P.shape[0]), xl)] == 0).all()
-        near = f["near_tf32"] if prec == "tf32" else (np.zeros_like(f["near_1e4"]) if prec in ("tf32x3", "fp64") else f["near_1e4"])
+        near = {"tf32-norefine": f["near_tf32"], "tf32x3-norefine": f["near_1e4"]}.get(prec, np.zeros_like(f["near_1e4"]))
         _check(f"C5 model {prec}", ex["counts"][xl], f["counts"], near)
         engine.release(3)
 

@@ -519,12 +519,16 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
     engine.set_grid(lo, hi, grid)
     m, v = engine.posterior(keep_v=keep_v)
     engine.sets(beta, capi.UNSAFE_ALL if rule == "all" else capi.UNSAFE_ANY)
-    ex = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)      # exact pruning on (the default)
-    engine.set_option("fantasy_prune", 0)                                             # every pair through the GEMM
+    # defaults: exact pruning on, FP64 refinement of the pairs inside the tensor-core error bound on
+    ex_ref = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
     try:
+        engine.set_option("fantasy_refine", 0)                                        # tensor-core decisions as they are
+        ex = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+        engine.set_option("fantasy_prune", 0)                                         # ... and every pair through the GEMM
         ex_all = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
     finally:
         engine.set_option("fantasy_prune", 1)
+        engine.set_option("fantasy_refine", 2)
         engine.set_option("fantasy_variant", -1)
     pts = oracle.make_grid(lo, hi, grid)
     lcb, _ = oracle.bounds(m, v, beta)
@@ -544,6 +548,12 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
     scale = sf2max * (1.0 + gain)[None, :]
     w64 = oracle.fantasy_counts(pts, ds, beta, S, Z)[S]
     out = {"newly_safe_fp64": int(w64.sum())}
+    # refined (the default): the counts are the FP64 counts; only a pair within FP64 rounding of the threshold may differ
+    exact = (margin <= 1e-12 * scale).sum(axis=0)
+    dr = np.abs(ex_ref["counts"][S].astype(np.int64) - w64)
+    assert np.all(dr <= exact), (precision, int(dr.max()), int((dr > exact).sum()))
+    assert ex_ref["n_ambiguous"] >= ex_ref["n_refined_safe"] >= 0
+    out.update(refined=int(ex_ref["n_ambiguous"]), refined_safe=int(ex_ref["n_refined_safe"]))
     assert np.all(got <= ex_all["counts"][S]) and ex["pairs_evaluated"] <= ex_all["pairs_evaluated"]
     if precision == "tf32":
         wtf = oracle.fantasy_counts(pts, ds, beta, S, Z, dtype="tf32")[S]
@@ -557,18 +567,10 @@ def _fantasy_tc_case(engine, oracle, ds, lo, hi, grid, beta, rule, variant, prec
         assert np.all(d2 <= amb), (int(d2.max()), int(amb.max()), int((d2 > amb).sum()))
         out.update(diff_vs_tf32_oracle=int(d1.sum()), diff_vs_fp64=int(d2.sum()), ambiguous=int(amb.sum()))
     else:
-        # split-TF32 + FP64 refinement of every pair inside the FP32 error bound (option fantasy_refine, default on): the
-        # counts are the FP64 counts; only a pair within FP64 rounding of the threshold may differ
-        exact = (margin <= 1e-12 * scale).sum(axis=0)
-        d2 = np.abs(got - w64)
-        assert np.all(d2 <= exact), (int(d2.max()), int(exact.max()), int((d2 > exact).sum()))
-        assert ex["n_ambiguous"] >= ex["n_refined_safe"] >= 0
-        # without the refinement the FP32 pipeline decides: differences only near the threshold
         amb = (margin <= IMPL_TOL * scale).sum(axis=0)
-        d3 = np.abs(ex_all["counts"][S].astype(np.int64) - w64)       # ex_all: un-pruned, refined as well
-        assert np.all(d3 <= exact)
-        out.update(diff_vs_fp64=int(d2.sum()), ambiguous_band=int(amb.sum()), refined=int(ex["n_ambiguous"]),
-                   refined_safe=int(ex["n_refined_safe"]))
+        d2 = np.abs(got - w64)
+        assert np.all(d2 <= amb), (int(d2.max()), int(amb.max()), int((d2 > amb).sum()))
+        out.update(diff_vs_fp64=int(d2.sum()), ambiguous=int(amb.sum()))
     return out
 
 
@@ -591,7 +593,7 @@ def test_fantasy_tensor_core_synthetic(engine, oracle, variant, precision):
         ds, lo, hi, pts_per_dim, beta = workloads.small(d=d, pts_per_dim=ppd, n=n, seed=7 + d, G=G)
         r = _fantasy_tc_case(engine, oracle, dict(ds), lo, hi, pts_per_dim, beta, "any", variant, precision)
         print(f"fantasy {precision} v{variant} synthetic d={d} n={n}: {r}")
-        if precision == "tf32x3":
+        if precision == "tf32x3":      # unrefined split mode
             assert r["diff_vs_fp64"] <= max(2, r["newly_safe_fp64"] // 1000)
 
 
