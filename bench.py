@@ -249,9 +249,11 @@ def reference_configs(eng, torch, reps=5, with_de=True):
 # dram__bytes_read.sum + dram__bytes_write.sum of k_fantasy_tc per launch from the committed ncu capture
 # (profiles/): filled in when a capture of the same configuration exists, else null
 TRAFFIC_NCU = {
-    # profiles/r01_ncu_final_summary.txt: tc::k_fantasy_tc2<1,4> on C4/TF32, one launch = the whole pair stage:
-    # 120.23 GB read + 0.29 GB written (z tiles are re-read once per x raster group; 3.4 % of HBM bandwidth)
-    ("c4", "tf32"): 120.23e9 + 0.289e9,
+    # profiles/r02_ncu_fantasy_tc2_tf32r_summary.csv: tc::k_fantasy_tc2<1,8,refine> on C4, single TF32 pass over the tile pairs the
+    # exact pruning keeps (one launch = the whole pair stage): 42.15 GB read + 0.04 GB written (3.2 % of the HBM bandwidth)
+    ("c4", "tf32"): 42.146603e9 + 0.040392e9,
+    # profiles/r02_ncu_fantasy_tc2_tf32x3_summary.csv (split operands, 2x the bytes per row): 227.7 GB read + 5.8 GB written
+    ("c4", "tf32x3"): 227.733712e9 + 5.802020e9,
 }
 
 

@@ -51,7 +51,7 @@ def test_c4_fantasy_counts_vs_full_size_oracle(engine):
     counts = {}
     for prec in ("tf32", "tf32-norefine", "tf32x3", "tf32x3-norefine", "fp64"):
         p, kv = capi.PRECISIONS[prec.split("-")[0]]
-        engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 1)
+        engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 2)
         engine.posterior(keep_v=kv, fetch=False)
         s = engine.sets(beta, capi.UNSAFE_ALL)
         assert s["n_safe"] == int(f["n_safe"]) and s["n_unsafe"] == int(f["n_unsafe"])
@@ -92,7 +92,7 @@ def test_c5_model_fantasy_counts_on_sampled_points(engine):
     xl = f["x_local"]
     for prec in ("tf32", "tf32-norefine", "tf32x3", "tf32x3-norefine", "fp64"):
         p, kv = capi.PRECISIONS[prec.split("-")[0]]
-        engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 1)
+        engine.set_option("fantasy_refine", 0 if prec.endswith("norefine") else 2)
         engine.posterior(keep_v=kv, fetch=False)
         s = engine.sets(beta, capi.UNSAFE_ALL)
         assert s["n_safe"] == int(f["n_safe"]) and s["n_unsafe"] == int(f["n_unsafe"])
