@@ -27,6 +27,7 @@ struct GridSpec {
 
 struct ModelSpec {
   int n, npad, d, G;
+  int g0;                   // posterior kernels process GPs g0 .. G-1 (0 except for the constraint-only FP64 rows of the refinement)
   const double* Xn;         // [npad][d], rows >= n are zero
   const double* alpha;      // [G][npad]
   const double* W;          // [G][npad][npad]  lower-triangular L^-1, zero elsewhere
@@ -142,6 +143,7 @@ struct sbo_ctx {
   GridSpec gs{};
   DevBuf pts;
   // posterior (local shard)
+  int post_g0 = 0;           // first GP the posterior kernels process (posterior_vrows_dev: constraints only)
   bool have_post = false, have_grad = false;   // have_grad: the last posterior accumulated the Lipschitz constants
   DevBuf mean, var, kx, lmax, tabs;     // tabs: separable SE-ARD factor tables of the meshgrid (posterior.cu)
   int keep_v = 0;            // 0 none, 1 fp64, 2 fp32

@@ -212,20 +212,21 @@ __device__ __forceinline__ uint32_t epilogue_chunk(const uint32_t (&acc)[32], co
   return w;
 }
 
-// Refining variant (split-TF32 mode).  E = ex*ez + e_abs bounds the error of the computed covariance (operand split,
-// one ulp of the running sum per tensor-core accumulation step, ex2.approx, FP32 records); d_mu / d_t bound the FP32
-// rounding of the mean and variance sides of the test.  The updated bound f(cov) = mu' - beta*sigma' is CONVEX in cov and
-// increasing for cov >= 0, so with lo = cov - E, hi = cov + E:
-//   U (settled unsafe)  <=  f is negative at lo AND at hi when evaluated OPTIMISTICALLY (+d_mu, -d_t): the maximum over the
-//                           interval is at an end;
-//   S (settled safe)    <=  lo >= 0 (monotone branch) and f is non-negative at lo evaluated PESSIMISTICALLY (-d_mu, +d_t).
+// Refining variant.  E = ex*ez + e_abs bounds the error of the computed covariance (operand rounding / split, one ulp
+// of the running sum per tensor-core accumulation step, ex2.approx, FP32 records); d_mu / d_t bound the FP32 rounding of
+// the mean and variance sides of the test.  The updated bound f(cov) = mu' - beta*sigma' is CONVEX in cov, satisfies
+// f(-c) <= f(c) (a_x >= 0) and increases for cov >= 0, so over the interval [cov - E, cov + E] it is bounded by
+// f(|cov| + E):
+//   U (settled unsafe)  <=  f(|cov| + E) < 0 evaluated OPTIMISTICALLY (+d_mu, -d_t)               -- ONE evaluation
+//   S (settled safe)    <=  cov - E >= 0 (monotone branch) and f(cov - E) >= 0 evaluated PESSIMISTICALLY (-d_mu, +d_t);
+//                           only needed where U fails: whole warps skip it (almost every pair is settled unsafe).
 // Everything else is AMBIGUOUS and goes to the FP64 re-evaluation (pairs.cu refine_ambiguous).
 template <int D4>
 __device__ __forceinline__ void epilogue_chunk_refine(const uint32_t (&acc)[32], const uint64_t* __restrict__ rec, const RowConsts<D4>& rc,
                                                       uint64_t e_abs2, uint64_t d_mu2, uint64_t d_t2, uint32_t& S, uint32_t& U) {
   constexpr int RS = 4 * D4 + 4;
   const uint64_t minus1 = pk2(-1.f, -1.f);
-  uint32_t wlo = 0, whi = 0, wsf = 0;
+  uint32_t wup = 0, wsf = 0;
 #pragma unroll
   for (int jp = 0; jp < 16; ++jp) {
     const uint64_t* p = rec + jp * RS;
@@ -238,31 +239,30 @@ __device__ __forceinline__ void epilogue_chunk_refine(const uint32_t (&acc)[32],
     const uint64_t a2 = pk2(__uint_as_float(acc[2 * jp]), __uint_as_float(acc[2 * jp + 1]));
     const uint64_t cov = fma2(a2, minus1, ex);
     const uint64_t E = fma2(rc.ex, p[4 * D4 + 3], e_abs2);                // ex*ez + e_abs
-    const uint64_t cl = fma2(E, minus1, cov), ch = add2(cov, E);
+    float c0, c1, E0, E1;
+    upk2(cov, c0, c1); upk2(E, E0, E1);
+    const uint64_t h = pk2(fabsf(c0) + E0, fabsf(c1) + E1);               // |cov| + E (the abs is an operand modifier)
     const uint64_t m_opt = add2(p[4 * D4 + 1], d_mu2);                    // m_z + d_mu
     const uint64_t s_opt = fma2(d_t2, minus1, p[4 * D4 + 2]);             // s'_z - d_t
-    const uint64_t cl2 = mul2(cl, cl), ch2 = mul2(ch, ch);
-    const uint64_t mu_lo = fma2(cl, rc.ax, m_opt), mu_hi = fma2(ch, rc.ax, m_opt);
-    const uint64_t t_lo = fma2(cl2, rc.nbx, s_opt), t_hi = fma2(ch2, rc.nbx, s_opt);
-    const uint64_t mm_lo = mul2(mu_lo, mu_lo), mm_hi = mul2(mu_hi, mu_hi);
-    float a0, a1, b0, b1, c0, c1, l0, l1;
+    const uint64_t mu_h = fma2(h, rc.ax, m_opt);
+    const uint64_t t_h = fma2(mul2(h, h), rc.nbx, s_opt);
+    const uint64_t mm_h = mul2(mu_h, mu_h);
+    float a0, a1, b0, b1, q0, q1;
     const uint32_t pairbits = 3u << (2 * jp);
-    upk2(mu_lo, a0, a1); upk2(t_lo, b0, b1); upk2(mm_lo, c0, c1);
-    set_bit_if_safe(wlo, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wlo, a1, c1, b1, 2u << (2 * jp));
-    upk2(mu_hi, a0, a1); upk2(t_hi, b0, b1); upk2(mm_hi, c0, c1);
-    set_bit_if_safe(whi, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(whi, a1, c1, b1, 2u << (2 * jp));
-    // the pessimistic evaluation only matters for pairs that are not already settled unsafe: almost none are, so the
-    // whole warp usually skips it (warp-uniform branch)
-    if (__any_sync(0xffffffffu, ((wlo | whi) & pairbits) != 0u)) {
+    upk2(mu_h, a0, a1); upk2(t_h, b0, b1); upk2(mm_h, q0, q1);
+    set_bit_if_safe(wup, a0, q0, b0, 1u << (2 * jp)); set_bit_if_safe(wup, a1, q1, b1, 2u << (2 * jp));
+    if (__any_sync(0xffffffffu, (wup & pairbits) != 0u)) {                // warp-uniform: some pair here is not settled unsafe
+      const uint64_t cl = fma2(E, minus1, cov);
       const uint64_t m_pes = fma2(d_mu2, minus1, p[4 * D4 + 1]), s_pes = add2(p[4 * D4 + 2], d_t2);   // m_z - d_mu, s'_z + d_t
-      const uint64_t mu_sf = fma2(cl, rc.ax, m_pes), t_sf = fma2(cl2, rc.nbx, s_pes), mm_sf = mul2(mu_sf, mu_sf);
-      upk2(mu_sf, a0, a1); upk2(t_sf, b0, b1); upk2(mm_sf, c0, c1); upk2(cl, l0, l1);
+      const uint64_t mu_sf = fma2(cl, rc.ax, m_pes), t_sf = fma2(mul2(cl, cl), rc.nbx, s_pes), mm_sf = mul2(mu_sf, mu_sf);
+      float l0, l1;
+      upk2(mu_sf, a0, a1); upk2(t_sf, b0, b1); upk2(mm_sf, q0, q1); upk2(cl, l0, l1);
       a0 = l0 < 0.f ? l0 : a0; a1 = l1 < 0.f ? l1 : a1;                   // lo < 0: not on the monotone branch -> never "settled safe"
-      set_bit_if_safe(wsf, a0, c0, b0, 1u << (2 * jp)); set_bit_if_safe(wsf, a1, c1, b1, 2u << (2 * jp));
+      set_bit_if_safe(wsf, a0, q0, b0, 1u << (2 * jp)); set_bit_if_safe(wsf, a1, q1, b1, 2u << (2 * jp));
     }
   }
   S = wsf;
-  U = ~wlo & ~whi;
+  U = ~wup;
 }
 
 // work item = one (x tile, z tile) pair, all constraints.  Items are ordered so that a group of GX x tiles sweeps

@@ -60,7 +60,7 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
   __shared__ double Xs[XC_JT * D];
   __shared__ double As[XC_JT];
   __shared__ double red[XC_THREADS / 32];
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + ms.g0;
   const int pl = blockIdx.x * XC_THREADS + threadIdx.x;
   const bool in_chunk = pl < P;
   const bool ok = pl < valid;
@@ -76,7 +76,7 @@ k_crosscov(ModelSpec ms, GridSpec gs, long long p0, int P, int valid, double* __
     for (int k = 0; k < D; ++k) xn[k] = (x[k] - ms.Xmean[k]) / ms.Xstd[k];       // GP_Safe.py:326
     if (ts.base) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) trow[k] = ts.base + (size_t)blockIdx.y * ts.goff + ts.koff[k] + (gp / gs.stride[k]) % gs.pts[k];
+      for (int k = 0; k < D; ++k) trow[k] = ts.base + (size_t)(blockIdx.y + ms.g0) * ts.goff + ts.koff[k] + (gp / gs.stride[k]) % gs.pts[k];
     }
   } else {
 #pragma unroll
@@ -164,7 +164,7 @@ k_solve_var(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, in
   __shared__ double Ws[PB_BK][PB_BM + 1];   // +1: conflict-free transposed stores
   __shared__ __align__(16) double Ks[PB_BK][PB_BP];
   __shared__ double red[16][PB_BP];
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + ms.g0;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int np = ms.npad;
@@ -280,7 +280,7 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
                  double* __restrict__ var_out, long long out_ld, void* __restrict__ vall, long long v_count) {
   extern __shared__ __align__(16) double dsm[];
   double* red = dsm + 2 * DV_STAGE;                 // [4][DV_BP]
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + ms.g0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tig = lane & 3;
   const int wr = warp & 3, wp = warp >> 2;          // warp tile: rows wr*32.., points wp*32..
@@ -406,7 +406,7 @@ k_solve_fused(ModelSpec ms, GridSpec gs, TabSpec ts, int EMIT, long long p0, int
               double* __restrict__ var_out, long long out_ld, void* __restrict__ vall, long long v_count) {
   extern __shared__ __align__(16) double dsm[];
   double* red = dsm + 2 * DV_STAGE;                 // [4][DV_BP]
-  const int g = blockIdx.y;
+  const int g = blockIdx.y + ms.g0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, tig = lane & 3;
   const int wr = warp & 3, wp = warp >> 2;          // warp tile: rows wr*32.., points wp*32..
@@ -545,8 +545,10 @@ k_solve_fused(ModelSpec ms, GridSpec gs, TabSpec ts, int EMIT, long long p0, int
 template <int D>
 static void launch_crosscov(sbo_ctx* ctx, const GridSpec& gs, long long p0, int P, int valid, double* Kx,
                             double* mean_out, long long out_ld, double* gradmax, double* grad_out, int grad_gp, const TabSpec& ts) {
-  dim3 grid((unsigned)cdiv(P, XC_THREADS), (unsigned)ctx->ms.G);
-  k_crosscov<D><<<grid, XC_THREADS, 0, ctx->stream>>>(ctx->ms, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax,
+  const int g0 = ctx->post_g0;
+  ModelSpec msl = ctx->ms; msl.g0 = g0;
+  dim3 grid((unsigned)cdiv(P, XC_THREADS), (unsigned)(ctx->ms.G - g0));
+  k_crosscov<D><<<grid, XC_THREADS, 0, ctx->stream>>>(msl, gs, p0, P, valid, Kx, mean_out, out_ld, gradmax,
                                                       grad_out, grad_gp, ts);
 }
 
@@ -569,29 +571,31 @@ static int crosscov_dispatch(sbo_ctx* ctx, const GridSpec& gs, long long p0, int
 
 static int solve_dispatch(sbo_ctx* ctx, const double* Kx, int P, long long p0, int valid, double* var_out,
                           long long out_ld, int keep_v, void* vall, long long v_count) {
+  const int g0 = ctx->post_g0;
+  ModelSpec msl = ctx->ms; msl.g0 = g0;
   if (ctx->opt_posterior_variant == 1) {   // FP64 tensor-core (DMMA) kernel
-    dim3 grid((unsigned)(P / DV_BP), (unsigned)ctx->ms.G);
+    dim3 grid((unsigned)(P / DV_BP), (unsigned)(ctx->ms.G - g0));
     // the attribute is per device and a process may hold contexts on several GPUs: set it before every launch
     SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
     SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
     SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
     SBO_CUDA(cudaFuncSetAttribute(k_solve_var_dmma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DV_SMEM));
-    if (keep_v == 1) k_solve_var_dmma<1><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
-    else if (keep_v == 2) k_solve_var_dmma<2><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
-    else if (keep_v == 3) k_solve_var_dmma<3><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
-    else k_solve_var_dmma<0><<<grid, 256, DV_SMEM, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
+    if (keep_v == 1) k_solve_var_dmma<1><<<grid, 256, DV_SMEM, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    else if (keep_v == 2) k_solve_var_dmma<2><<<grid, 256, DV_SMEM, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    else if (keep_v == 3) k_solve_var_dmma<3><<<grid, 256, DV_SMEM, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    else k_solve_var_dmma<0><<<grid, 256, DV_SMEM, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
     SBO_LAUNCH_CHECK();
     return SBO_OK;
   }
-  dim3 grid((unsigned)(P / PB_BP), (unsigned)ctx->ms.G);
+  dim3 grid((unsigned)(P / PB_BP), (unsigned)(ctx->ms.G - g0));
   if (keep_v == 1)
-    k_solve_var<1><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    k_solve_var<1><<<grid, 256, 0, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
   else if (keep_v == 2)
-    k_solve_var<2><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    k_solve_var<2><<<grid, 256, 0, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
   else if (keep_v == 3)
-    k_solve_var<3><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
+    k_solve_var<3><<<grid, 256, 0, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, vall, v_count);
   else
-    k_solve_var<0><<<grid, 256, 0, ctx->stream>>>(ctx->ms, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
+    k_solve_var<0><<<grid, 256, 0, ctx->stream>>>(msl, Kx, P, p0, valid, var_out, out_ld, nullptr, 0);
   SBO_LAUNCH_CHECK();
   return SBO_OK;
 }
@@ -756,14 +760,15 @@ int posterior_vrows_dev(sbo_ctx* ctx, long long m, const double* pts_dev, double
   SBO_TRY(sbo_ensure(ctx, ctx->pp_v, sizeof(double) * (size_t)ms.G * m));
   const long long P = chunk_points(ctx, ms, m);
   SBO_TRY(sbo_ensure(ctx, ctx->pp_k, sizeof(double) * (size_t)ms.G * ms.npad * P));
-  const int64_t keep_variant = ctx->opt_posterior_variant;
-  for (long long p0 = 0; p0 < m; p0 += P) {
+  ctx->post_g0 = ms.G > 1 ? 1 : 0;               // the objective GP's rows are not needed
+  int rc = SBO_OK;
+  for (long long p0 = 0; p0 < m && rc == SBO_OK; p0 += P) {
     const int valid = (int)((m - p0) < P ? (m - p0) : P);
-    SBO_TRY(crosscov_dispatch(ctx, tmp, p0, (int)P, valid, (double*)ctx->pp_k.p, (double*)ctx->pp_m.p, m, nullptr, nullptr, -1));
-    SBO_TRY(solve_dispatch(ctx, (const double*)ctx->pp_k.p, (int)P, p0, valid, (double*)ctx->pp_v.p, m, 1, vout, m));
+    rc = crosscov_dispatch(ctx, tmp, p0, (int)P, valid, (double*)ctx->pp_k.p, (double*)ctx->pp_m.p, m, nullptr, nullptr, -1);
+    if (rc == SBO_OK) rc = solve_dispatch(ctx, (const double*)ctx->pp_k.p, (int)P, p0, valid, (double*)ctx->pp_v.p, m, 1, vout, m);
   }
-  (void)keep_variant;
-  return SBO_OK;
+  ctx->post_g0 = 0;
+  return rc;
 }
 
 int posterior_point_grad(sbo_ctx* ctx, int gp, int64_t m, const double* x, double* grad) {
