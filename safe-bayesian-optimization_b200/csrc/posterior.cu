@@ -329,24 +329,27 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
       __syncthreads();
       const double* Ws = dsm + (kc & 1) * DV_STAGE;
       const double* Ks = Ws + DV_BM * DV_WS;
-      // W is lower triangular: this warp's 32 rows need columns <= rb*128 + wr*32 + 31 only, i.e. K chunks
-      // kc <= rb*4 + wr; the later chunks of the diagonal block are all zeros for it
-      if (kc <= rb * (DV_BM / DV_BK) + wr)
+      // W is lower triangular: rows of quarter i (32 rows) of the block need columns <= rb*128 + i*32 + 31 only, i.e. K
+      // chunks kc <= rb*4 + i.  Every warp owns 8 rows of EACH quarter (fragment i = rows i*32 + wr*8 .. +7), so in the
+      // diagonal block all warps skip the same zero fragments: 10 fragment-chunks each instead of 4/8/12/16 per warp.
+      const int iq = kc - rb * (DV_BM / DV_BK);        // quarter index of this chunk inside the diagonal block (<= 0 before it)
 #pragma unroll
       for (int k0 = 0; k0 < DV_BK; k0 += 4) {
         double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = Ws[(wr * 32 + i * 8 + grp) * DV_WS + k0 + tig];
+        for (int i = 0; i < 4; ++i) a[i] = Ws[(i * 32 + wr * 8 + grp) * DV_WS + k0 + tig];
 #pragma unroll
         for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
+          if (i >= iq) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          }
       }
       __syncthreads();
     }
-    // row-block epilogue: acc[i][j][e] = v[row = rb*128 + wr*32 + i*8 + grp][point = wp*32 + j*8 + 2*tig + e]
+    // row-block epilogue: acc[i][j][e] = v[row = rb*128 + i*32 + wr*8 + grp][point = wp*32 + j*8 + 2*tig + e]
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -356,18 +359,18 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
         if (emit) {
           const long long pl = (long long)blockIdx.x * DV_BP + wp * 32 + j * 8 + 2 * tig + e;
           if (pl < valid) {
-            const size_t rowbase = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * DV_BM + wr * 32 + grp;
+            const size_t rowbase = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * DV_BM + wr * 8 + grp;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const double v = acc[i][j][e];
               if (EMIT == 1) {
-                reinterpret_cast<double*>(vall)[rowbase + i * 8] = v;
+                reinterpret_cast<double*>(vall)[rowbase + i * 32] = v;
               } else if (EMIT == 2) {
-                reinterpret_cast<float*>(vall)[rowbase + i * 8] = to_tf32((float)v);
+                reinterpret_cast<float*>(vall)[rowbase + i * 32] = to_tf32((float)v);
               } else {
                 const float hi = to_tf32((float)v);
-                reinterpret_cast<float*>(vall)[rowbase + i * 8] = hi;
-                reinterpret_cast<float*>(vall)[rowbase + i * 8 + np] = to_tf32((float)(v - (double)hi));
+                reinterpret_cast<float*>(vall)[rowbase + i * 32] = hi;
+                reinterpret_cast<float*>(vall)[rowbase + i * 32 + np] = to_tf32((float)(v - (double)hi));
               }
             }
           }
@@ -472,24 +475,27 @@ k_solve_fused(ModelSpec ms, GridSpec gs, TabSpec ts, int EMIT, long long p0, int
       __syncthreads();
       const double* Ws = dsm + (kc & 1) * DV_STAGE;
       const double* Ks = Ws + DV_BM * DV_WS;
-      // W is lower triangular: this warp's 32 rows need columns <= rb*128 + wr*32 + 31 only, i.e. K chunks
-      // kc <= rb*4 + wr; the later chunks of the diagonal block are all zeros for it
-      if (kc <= rb * (DV_BM / DV_BK) + wr)
+      // W is lower triangular: rows of quarter i (32 rows) of the block need columns <= rb*128 + i*32 + 31 only, i.e. K
+      // chunks kc <= rb*4 + i.  Every warp owns 8 rows of EACH quarter (fragment i = rows i*32 + wr*8 .. +7), so in the
+      // diagonal block all warps skip the same zero fragments: 10 fragment-chunks each instead of 4/8/12/16 per warp.
+      const int iq = kc - rb * (DV_BM / DV_BK);        // quarter index of this chunk inside the diagonal block (<= 0 before it)
 #pragma unroll
       for (int k0 = 0; k0 < DV_BK; k0 += 4) {
         double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = Ws[(wr * 32 + i * 8 + grp) * DV_WS + k0 + tig];
+        for (int i = 0; i < 4; ++i) a[i] = Ws[(i * 32 + wr * 8 + grp) * DV_WS + k0 + tig];
 #pragma unroll
         for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
+          if (i >= iq) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          }
       }
       __syncthreads();
     }
-    // row-block epilogue: acc[i][j][e] = v[row = rb*128 + wr*32 + i*8 + grp][point = wp*32 + j*8 + 2*tig + e]
+    // row-block epilogue: acc[i][j][e] = v[row = rb*128 + i*32 + wr*8 + grp][point = wp*32 + j*8 + 2*tig + e]
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -499,18 +505,18 @@ k_solve_fused(ModelSpec ms, GridSpec gs, TabSpec ts, int EMIT, long long p0, int
         if (emit) {
           const long long pl = (long long)blockIdx.x * DV_BP + wp * 32 + j * 8 + 2 * tig + e;
           if (pl < valid) {
-            const size_t rowbase = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * DV_BM + wr * 32 + grp;
+            const size_t rowbase = ((size_t)(g - 1) * v_count + p0 + pl) * (EMIT == 3 ? 2 * np : np) + rb * DV_BM + wr * 8 + grp;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const double v = acc[i][j][e];
               if (EMIT == 1) {
-                reinterpret_cast<double*>(vall)[rowbase + i * 8] = v;
+                reinterpret_cast<double*>(vall)[rowbase + i * 32] = v;
               } else if (EMIT == 2) {
-                reinterpret_cast<float*>(vall)[rowbase + i * 8] = to_tf32((float)v);
+                reinterpret_cast<float*>(vall)[rowbase + i * 32] = to_tf32((float)v);
               } else {
                 const float hi = to_tf32((float)v);
-                reinterpret_cast<float*>(vall)[rowbase + i * 8] = hi;
-                reinterpret_cast<float*>(vall)[rowbase + i * 8 + np] = to_tf32((float)(v - (double)hi));
+                reinterpret_cast<float*>(vall)[rowbase + i * 32] = hi;
+                reinterpret_cast<float*>(vall)[rowbase + i * 32 + np] = to_tf32((float)(v - (double)hi));
               }
             }
           }

@@ -174,8 +174,6 @@ __global__ void __launch_bounds__(ST)
 k_sets_pass1_v4(long long count, GridSpec gs, const double* __restrict__ mean, const double* __restrict__ var,
                 double beta, int rule, int strict, uint32_t* __restrict__ safe_w, uint32_t* __restrict__ unsafe_w,
                 SetsPartial* __restrict__ part) {
-  __shared__ ArgVal sm_av[ST / 32];
-  __shared__ long long sm_ll[ST / 32];
   const int lane = threadIdx.x & 31;
   ArgVal u{INFINITY, SBO_IDX_NONE}, l{INFINITY, SBO_IDX_NONE};
   long long ns = 0, nu = 0;
@@ -209,11 +207,23 @@ k_sets_pass1_v4(long long count, GridSpec gs, const double* __restrict__ mean, c
     const uint32_t ws = nibble_to_word(sb, lane), wu = nibble_to_word(ub, lane);
     if ((lane & 7) == 0 && p < count) { safe_w[p >> 5] = ws; unsafe_w[p >> 5] = wu; }
   }
-  u = block_argmin(u, sm_av);
-  l = block_argmin(l, sm_av);
-  ns = block_sum_ll(ns, sm_ll);
-  nu = block_sum_ll(nu, sm_ll);
-  if (threadIdx.x == 0) part[blockIdx.x] = SetsPartial{u.v, u.i, l.v, l.i, ns, nu};
+  // one shared-memory exchange for the four block reductions (a single barrier instead of eight: the reductions are the
+  // serial tail of a bandwidth-bound CTA)
+  __shared__ ArgVal sm_u[ST / 32], sm_l[ST / 32];
+  __shared__ long long sm_s[ST / 32], sm_n[ST / 32];
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    u = argmin2(u, shfl_xor_argval(u, m));
+    l = argmin2(l, shfl_xor_argval(l, m));
+    ns += __shfl_xor_sync(0xffffffffu, ns, m);
+    nu += __shfl_xor_sync(0xffffffffu, nu, m);
+  }
+  if (lane == 0) { sm_u[threadIdx.x >> 5] = u; sm_l[threadIdx.x >> 5] = l; sm_s[threadIdx.x >> 5] = ns; sm_n[threadIdx.x >> 5] = nu; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < ST / 32; ++w) { u = argmin2(u, sm_u[w]); l = argmin2(l, sm_l[w]); ns += sm_s[w]; nu += sm_n[w]; }
+    part[blockIdx.x] = SetsPartial{u.v, u.i, l.v, l.i, ns, nu};
+  }
 }
 
 __global__ void __launch_bounds__(ST)
