@@ -136,7 +136,7 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   // (3) reference-exact mode: grid order of the gathered candidates; SafeOpt expander split by candidates
   if (!fantasy && R > 1) {
     SBO_TRY(pairs_set_segments(ctx, R, rank, n_all.data()));
-    if (!goose) {
+    {   // SafeOpt expander: split by candidates; GoOSE target: split by (grid-ordered) unsafe tiles -- both over ALL unsafe points
       double w1 = (double)mask_words(ctx);
       SBO_TRY(gather_record(ctx, &w1, 1, g));
       long long wpr = 0;
@@ -152,15 +152,25 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   SBO_TRY(pairs_import(ctx, n_total, rows, vrows));
   if (big) { SBO_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(cm->vrows.p); ctx->mem_now -= (int64_t)cm->vrows.cap; cm->vrows.p = nullptr; cm->vrows.cap = 0; }
   // (4) run on the local shard, combine the per-candidate results
-  const size_t res_b = fantasy ? sizeof(int) * (size_t)n_total : (size_t)nc * (size_t)(goose ? info.n_z_local : n_total);
-  SBO_TRY(sbo_ensure(ctx, cm->result, res_b ? res_b : 16));
+  const long long nzg = ctx->ps.nz_global;                     // >= 0: the pair stage runs over the all-gathered unsafe set
+  const bool goose_global = goose && nzg >= 0;
+  const size_t res_b = fantasy ? sizeof(int) * (size_t)n_total
+                               : (size_t)nc * (size_t)(goose ? (goose_global ? nzg : info.n_z_local) : n_total);
+  SBO_TRY(sbo_ensure(ctx, cm->result, (res_b ? res_b : 16) + (goose_global ? (size_t)nc * info.n_z_local + 16 : 0)));
   SBO_TRY(pairs_run(ctx, goose ? 1 : 0, cm->result.p));
   if (!goose && n_total > 0) {
     if (fantasy) SBO_NCCL(g_nccl.AllReduce(cm->result.p, cm->result.p, (size_t)n_total, ncclInt32, ncclSum, NC(ctx), ctx->stream));
     else SBO_NCCL(g_nccl.AllReduce(cm->result.p, cm->result.p, (size_t)nc * n_total, ncclUint8, ncclMax, NC(ctx), ctx->stream));
   }
+  const void* res_ptr = cm->result.p;
+  if (goose_global && nzg > 0 && n_total > 0) {
+    SBO_NCCL(g_nccl.AllReduce(cm->result.p, cm->result.p, (size_t)nc * nzg, ncclUint8, ncclMax, NC(ctx), ctx->stream));
+    unsigned char* local = (unsigned char*)cm->result.p + (((size_t)nc * nzg + 15) & ~(size_t)15);
+    SBO_TRY(pairs_goose_localize(ctx, cm->result.p, local));
+    res_ptr = local;
+  }
   sbo_pair_result loc;
-  SBO_TRY(pairs_finish(ctx, goose ? 1 : 0, goose ? 0 : offset, cm->result.p, &loc, nullptr));
+  SBO_TRY(pairs_finish(ctx, goose ? 1 : 0, goose ? 0 : offset, res_ptr, &loc, nullptr));
   // (5) global optima: per constraint (value, index), then the first best over the constraints (SafeOpt.py:120-122)
   const int nmask = fantasy ? 1 : nc;
   const int nrec = 2 * SBO_MAX_G + 4;

@@ -247,6 +247,7 @@ int pairs_export(sbo_ctx* ctx, void* rows_dev, void* vrows_dev);
 int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const void* vrows_dev);
 int pairs_run(sbo_ctx* ctx, int goose, void* result_dev);
 int pairs_set_segments(sbo_ctx* ctx, int nranks, int rank, const int64_t* n_per_rank);
+int pairs_goose_localize(sbo_ctx* ctx, const void* hits_global, void* hits_local);
 int pairs_set_global_unsafe(sbo_ctx* ctx, const void* gathered_words_dev, long long words_per_rank, int nranks);
 int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_dev, sbo_pair_result* out, int32_t* counts_host);
 int pairs_fantasy(sbo_ctx* ctx, int precision, double beta, sbo_pair_result* out, int32_t* counts_host);

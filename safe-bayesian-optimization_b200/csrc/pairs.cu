@@ -179,11 +179,12 @@ __global__ void __launch_bounds__(PT)
 k_pairs_target(PairConsts pc, long long nx, long long nz, const double* __restrict__ xc, const double* __restrict__ ucb,
                const double* __restrict__ thr, const double* __restrict__ zc, unsigned char* __restrict__ hits,
                unsigned long long* __restrict__ pair_counter, long long x_per_split, const double* __restrict__ bb,
-               long long ntiles) {
+               long long ntiles, int tile_stride, int tile_offset) {
   __shared__ double xs[D][PT];
   __shared__ double us[SBO_MAX_G - 1][PT];
   __shared__ double rs[SBO_MAX_G - 1][PT];
-  const long long t = (long long)blockIdx.x * PT + threadIdx.x;
+  // sharded runs over the all-gathered unsafe set: z tiles are dealt round-robin to the ranks
+  const long long t = ((long long)blockIdx.x * tile_stride + tile_offset) * PT + threadIdx.x;
   const bool active = t < nz;
   double z[D];
   const unsigned full = (1u << pc.nc) - 1u;
@@ -255,7 +256,7 @@ static int launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long lon
                         unsigned long long* ctr, int tile_stride, int tile_offset, const int* out_pos) {
   const long long nthr = goose ? nz : nx, ntile = goose ? nx : nz;
   long long bx = cdiv(nthr, PT);
-  if (!goose && tile_stride > 1) bx = bx > tile_offset ? cdiv(bx - tile_offset, tile_stride) : 0;   // this rank's candidate tiles
+  if (tile_stride > 1) bx = bx > tile_offset ? cdiv(bx - tile_offset, tile_stride) : 0;   // this rank's share of the thread-side tiles
   if (bx == 0) return SBO_OK;
   long long splits = 1;
   const long long tiles = cdiv(ntile, PT);
@@ -274,7 +275,8 @@ static int launch_pairs(sbo_ctx* ctx, bool goose, const PairConsts& pc, long lon
     ctx->launches++;
   }
   if (goose)
-    k_pairs_target<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles);
+    k_pairs_target<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles,
+                                                    tile_stride > 1 ? tile_stride : 1, tile_stride > 1 ? tile_offset : 0);
   else
     k_pairs_expander<D><<<grid, PT, 0, ctx->stream>>>(pc, nx, nz, xc, ucb, thr, zc, hits, ctr, per, bb, tiles,
                                                       tile_stride > 1 ? tile_stride : 1, tile_stride > 1 ? tile_offset : 0, out_pos);
@@ -1171,6 +1173,30 @@ int pairs_import(sbo_ctx* ctx, long long n_total, const void* rows_dev, const vo
   return SBO_OK;
 }
 
+// sharded GoOSE target over the global unsafe list: flags of THIS rank's unsafe points, hits_local[c][t] = hits_global[c][pos]
+// with pos = position of local point zs_idx[t] in the ascending global list (binary search)
+__global__ void __launch_bounds__(256)
+k_goose_localize(GridSpec gs, int nc, long long nz_local, const long long* __restrict__ zs_idx, const long long* __restrict__ gz_idx,
+                 long long nz_global, const unsigned char* __restrict__ hg, unsigned char* __restrict__ hl) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nz_local) return;
+  const long long g = shard_global(gs, zs_idx[t]);
+  long long lo = 0, hi = nz_global;
+  while (lo < hi) { const long long m = (lo + hi) >> 1; if (gz_idx[m] < g) lo = m + 1; else hi = m; }
+  for (int c = 0; c < nc; ++c) hl[(size_t)c * nz_local + t] = (lo < nz_global && gz_idx[lo] == g) ? hg[(size_t)c * nz_global + lo] : 0;
+}
+int pairs_goose_localize(sbo_ctx* ctx, const void* hits_global, void* hits_local) {
+  PairStage& ps = ctx->ps;
+  SBO_REQUIRE(ps.prepared && ps.nz_global >= 0, "pairs_goose_localize: no global unsafe set");
+  const int nc = ctx->ms.G - 1;
+  if (ps.nz_local == 0 || nc == 0) return SBO_OK;
+  k_goose_localize<<<(unsigned)cdiv(ps.nz_local, 256), 256, 0, ctx->stream>>>(ctx->gs, nc, ps.nz_local, (const long long*)ctx->zs_idx.p,
+                                                                               (const long long*)ctx->gz_idx.p, ps.nz_global,
+                                                                               (const unsigned char*)hits_global, (unsigned char*)hits_local);
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
 int pairs_set_segments(sbo_ctx* ctx, int nranks, int rank, const int64_t* n_per_rank) {
   PairStage& ps = ctx->ps;
   SBO_REQUIRE(ps.prepared, "sbo_pairs_set_segments: call sbo_pairs_prepare first");
@@ -1225,12 +1251,13 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
   ps.pairs_evaluated = 0;
   ps.counted = false;
   if (nc == 0) return SBO_OK;
-  const size_t res_bytes = (ps.mode == SBO_MODE_FANTASY) ? sizeof(int) * (size_t)nx : (size_t)nc * (goose ? nz : nx);
+  const size_t res_bytes = (ps.mode == SBO_MODE_FANTASY) ? sizeof(int) * (size_t)nx
+                                                         : (size_t)nc * (goose ? (ps.nz_global >= 0 ? ps.nz_global : nz) : nx);
   if (res_bytes) {
     SBO_REQUIRE(result_dev != nullptr, "null result buffer");
     SBO_CUDA(cudaMemsetAsync(result_dev, 0, res_bytes, ctx->stream));
   }
-  if (nx == 0 || (nz == 0 && !(ps.nz_global > 0 && !goose))) return SBO_OK;
+  if (nx == 0 || (nz == 0 && !(ps.nz_global > 0))) return SBO_OK;
   SBO_TRY(sbo_ensure(ctx, ctx->pairctr, 2 * sizeof(unsigned long long)));
   SBO_CUDA(cudaMemsetAsync(ctx->pairctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
   unsigned long long* ctr = (unsigned long long*)ctx->pairctr.p;
@@ -1242,7 +1269,9 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
     for (int c = 0; c < nc; ++c) pc.L[c] = ps.L[c];
     // sharded SafeOpt expander: ALL unsafe points in grid order (sbo_pairs_set_global_unsafe_dev), this rank's share
     // of the candidate tiles; GoOSE target and single-GPU runs: the local unsafe points, every candidate
-    const bool by_cand = !goose && ps.nz_global >= 0;
+    // sharded GoOSE target with the all-gathered unsafe set: this rank's share of the (grid-ordered, compact) z tiles against
+    // every candidate; result_dev then holds nc x nz_global flags indexed by the position in the global unsafe list
+    const bool by_cand = ps.nz_global >= 0;
     const double* zc = (const double*)(by_cand ? ctx->gz_pay.p : ctx->zs_pay.p);
     const long long nzr = by_cand ? ps.nz_global : nz;
     const int stride = by_cand ? ps.seg_n : 1, off = by_cand ? ps.seg_rank : 0;

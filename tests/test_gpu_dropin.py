@@ -327,3 +327,17 @@ def test_stableopt_minmax_on_the_grid(oracle):
     assert bo.Minimise_d(bo.lcb, xc, 2) == pytest.approx(np.min(mo[:, 2] - beta * np.sqrt(vo[:, 2])), rel=1e-9)
     bo.engine.set_option("prior_mean_zero", 0)
     bo.engine.close()
+
+
+def test_lipschitz_needs_a_posterior_with_gradients(engine):
+    """sbo_lipschitz after sbo_posterior(with_grad=0) must fail instead of returning zeros (L = 0 would make every
+    safe point 'reach' every unsafe point)."""
+    from sbo_b200 import workloads
+    ds, lo, hi, pts, beta = workloads.small(d=3, pts_per_dim=8, n=30, seed=2, G=3)
+    engine.set_model(ds)
+    engine.set_grid(lo, hi, pts)
+    engine.posterior(with_grad=False, fetch=False)
+    with pytest.raises(ValueError):
+        engine.lipschitz()
+    engine.posterior(with_grad=True, fetch=False)
+    assert np.all(engine.lipschitz()[1:] > 0)

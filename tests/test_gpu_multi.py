@@ -41,3 +41,24 @@ def test_two_gpus_agree_with_one(mode, precision, orchestrator):
             assert a[k] == b[k], (kind, k)
         if kind == "safeopt":        # split by candidates: the early exit and the culling do the single-GPU work, shared
             assert b["pairs_evaluated"] <= 1.1 * a["pairs_evaluated"] + 4 * 256 * 256 * 3
+
+
+def test_two_contexts_on_two_devices_in_one_process(oracle):
+    """the >48 KB dynamic shared-memory opt-in is per device.  One process, one context per GPU: the DMMA posterior
+    (112 KB) and the tcgen05 fantasy GEMM must launch on both and agree."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sbo_b200
+    from sbo_b200 import _capi as capi, workloads
+    ds, lo, hi, pts, beta = workloads.small(d=4, pts_per_dim=9, n=200, seed=11, G=4)
+    res = []
+    for dev in (1, 0, 1):                       # device 1 first: a process-wide flag set by device 0 would hide the bug
+        eng = sbo_b200.GridEngine(dev)
+        eng.set_grid(lo, hi, pts)
+        st = eng.safeopt_step(ds, beta, mode="fantasy", precision="tf32", unsafe_rule=capi.UNSAFE_ANY)
+        m, v = eng.posterior()
+        res.append((st["n_safe"], st["x_new_idx"], st["expander"]["n_hit"], float(m.sum()), float(v.sum())))
+        eng.close()
+    assert res[0] == res[1] == res[2]

@@ -248,3 +248,28 @@ def test_trust_region_update_rule():
     bo.grid_shape = (5, 3)
     m = bo._ball_mask([1.5, 1.0], 0.6).reshape(3, 5)
     assert m[2, 4] and m[2, 3] and not m[2, 2] and not m[1, 4] and m.sum() == 2
+
+
+def test_drivers_stop_on_an_empty_safe_set_instead_of_sampling_nan():
+    """with no safe grid point the acquisition functions return NaN coordinates; the drivers must not evaluate the
+    plant there (it would poison the normalisation and the factor of every later iteration)."""
+    import sbo_b200  # noqa: F401
+    from sbo_b200 import drivers
+
+    class Empty:
+        n_fun, nx_dim = 2, 2
+        def Minimizer(self): return np.full(2, np.nan), 0.0
+        def Expander(self): return np.full(2, np.nan), 0.0
+        def minimize_obj_lcb(self): return np.full(2, np.nan), np.inf
+        def Target(self): return np.full(2, np.nan), np.inf
+        def explore_safeset(self, t): return np.full(2, np.nan)
+
+    with pytest.raises(drivers.EmptySafeSet):
+        drivers.safeopt_iteration(Empty())
+    with pytest.raises(drivers.EmptySafeSet):
+        drivers.goose_iteration(Empty())
+
+    class OnlyExpander(Empty):
+        def Expander(self): return np.array([0.1, 0.2]), 0.0
+    x, info = drivers.safeopt_iteration(OnlyExpander())        # std tie -> "expander" branch is NaN-free
+    assert np.allclose(x, [0.1, 0.2])
