@@ -550,6 +550,7 @@ def run_ours(args):
                        "value_counts": "all |S|*|Z|*(G-1) pairs: the exact pruning decides the skipped ones without evaluating them",
                        "l2": "256 MiB flush buffer written between timed steps; working set >> L2",
                        "excludes": "plant evaluation and hyper-parameter fit (host side in the reference too)"},
+            "value_evaluated_pairs_only": int(ex["pairs_evaluated"]) / (ms * 1e-3),
             "phase_ms": ph, "clocks": clk, "gpu_launches": int(launches // max(1, args.steps)),
             "e2e": {"value": pairs / e2e_s, "unit": "pair-evals/s", "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

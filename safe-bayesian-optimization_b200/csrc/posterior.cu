@@ -274,6 +274,25 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+
+// one K chunk of the DMMA solve for fragments I0..3 of the warp (fragment i = rows i*32 + wr*8 .. +7 of the row block)
+template <int I0>
+__device__ __forceinline__ void dv_chunk(double (&acc)[4][4][2], const double* __restrict__ Ws, const double* __restrict__ Ks,
+                                         int wr, int wp, int grp, int tig) {
+#pragma unroll
+  for (int k0 = 0; k0 < DV_BK; k0 += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = I0; i < 4; ++i) a[i] = Ws[(i * 32 + wr * 8 + grp) * DV_WS + k0 + tig];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
+#pragma unroll
+    for (int i = I0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
 template <int EMIT>
 __global__ void __launch_bounds__(256, 2)
 k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p0, int valid,
@@ -311,6 +330,8 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
   };
 
   const int nrb = np / DV_BM;
+  int it = 0;                                       // chunk counter over ALL row blocks: the ring never drains between them
+  load_chunk(0, 0, 0);
   for (int rb = 0; rb < nrb; ++rb) {
     double acc[4][4][2];
 #pragma unroll
@@ -318,35 +339,29 @@ k_solve_var_dmma(ModelSpec ms, const double* __restrict__ Kx, int P, long long p
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int nk = (rb + 1) * DV_BM / DV_BK;
-    load_chunk(0, rb, 0);
-    for (int kc = 0; kc < nk; ++kc) {
-      if (kc + 1 < nk) {
-        load_chunk((kc + 1) & 1, rb, (kc + 1) * DV_BK);
+    for (int kc = 0; kc < nk; ++kc, ++it) {
+      // prefetch the successor chunk -- the first chunk of the NEXT row block after the last one of this block, so that
+      // it lands while this block's epilogue (|v|^2, V rows) runs
+      const bool last = kc + 1 == nk;
+      if (!last || rb + 1 < nrb) {
+        load_chunk((it + 1) & 1, last ? rb + 1 : rb, last ? 0 : (kc + 1) * DV_BK);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
       } else {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncthreads();
-      const double* Ws = dsm + (kc & 1) * DV_STAGE;
+      const double* Ws = dsm + (it & 1) * DV_STAGE;
       const double* Ks = Ws + DV_BM * DV_WS;
       // W is lower triangular: rows of quarter i (32 rows) of the block need columns <= rb*128 + i*32 + 31 only, i.e. K
       // chunks kc <= rb*4 + i.  Every warp owns 8 rows of EACH quarter (fragment i = rows i*32 + wr*8 .. +7), so in the
       // diagonal block all warps skip the same zero fragments: 10 fragment-chunks each instead of 4/8/12/16 per warp.
       const int iq = kc - rb * (DV_BM / DV_BK);        // quarter index of this chunk inside the diagonal block (<= 0 before it)
-#pragma unroll
-      for (int k0 = 0; k0 < DV_BK; k0 += 4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = Ws[(i * 32 + wr * 8 + grp) * DV_WS + k0 + tig];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i >= iq) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-          }
-      }
+      // real (warp-uniform) branches over compile-time fragment ranges: a predicated-off DMMA still occupies the FP64
+      // tensor pipe (measured: ptxas predicates `if (i >= iq)`, and the kernel time does not move)
+      if (iq <= 0) dv_chunk<0>(acc, Ws, Ks, wr, wp, grp, tig);
+      else if (iq == 1) dv_chunk<1>(acc, Ws, Ks, wr, wp, grp, tig);
+      else if (iq == 2) dv_chunk<2>(acc, Ws, Ks, wr, wp, grp, tig);
+      else dv_chunk<3>(acc, Ws, Ks, wr, wp, grp, tig);
       __syncthreads();
     }
     // row-block epilogue: acc[i][j][e] = v[row = rb*128 + i*32 + wr*8 + grp][point = wp*32 + j*8 + 2*tig + e]
@@ -479,20 +494,12 @@ k_solve_fused(ModelSpec ms, GridSpec gs, TabSpec ts, int EMIT, long long p0, int
       // chunks kc <= rb*4 + i.  Every warp owns 8 rows of EACH quarter (fragment i = rows i*32 + wr*8 .. +7), so in the
       // diagonal block all warps skip the same zero fragments: 10 fragment-chunks each instead of 4/8/12/16 per warp.
       const int iq = kc - rb * (DV_BM / DV_BK);        // quarter index of this chunk inside the diagonal block (<= 0 before it)
-#pragma unroll
-      for (int k0 = 0; k0 < DV_BK; k0 += 4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = Ws[(i * 32 + wr * 8 + grp) * DV_WS + k0 + tig];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Ks[(k0 + tig) * DV_KS + wp * 32 + j * 8 + grp];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i >= iq) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-          }
-      }
+      // real (warp-uniform) branches over compile-time fragment ranges: a predicated-off DMMA still occupies the FP64
+      // tensor pipe (measured: ptxas predicates `if (i >= iq)`, and the kernel time does not move)
+      if (iq <= 0) dv_chunk<0>(acc, Ws, Ks, wr, wp, grp, tig);
+      else if (iq == 1) dv_chunk<1>(acc, Ws, Ks, wr, wp, grp, tig);
+      else if (iq == 2) dv_chunk<2>(acc, Ws, Ks, wr, wp, grp, tig);
+      else dv_chunk<3>(acc, Ws, Ks, wr, wp, grp, tig);
       __syncthreads();
     }
     // row-block epilogue: acc[i][j][e] = v[row = rb*128 + i*32 + wr*8 + grp][point = wp*32 + j*8 + 2*tig + e]
