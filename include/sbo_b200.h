@@ -244,6 +244,8 @@ int64_t sbo_mem_peak(sbo_ctx* ctx, int reset);
 int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
 /* tuning / diagnosis options (defaults reproduce the documented behaviour; none changes a result):
  *   "posterior_variant"  1 (default) FP64 tensor cores (DMMA) | 0 FP64 SIMT register tiles
+ *   "posterior_tables"   1: on meshgrids the cross-covariance kernel multiplies separable SE-ARD factor tables instead of calling
+ *                        exp() per entry (same values to ~1e-16 relative; measured slower, 13.5 vs 9.0 ms at C4) | 0 (default)
  *   "posterior_fused"    1: meshgrids use separable SE-ARD factor tables; the cross-covariance is generated inside the solve
  *                        kernel's shared-memory stage and never stored (C4: 12 MB of DRAM traffic instead of 33.6 GB, 52.5 ms
  *                        instead of 40.0 ms) | 0 (default): cross-covariance kernel + scratch + solve

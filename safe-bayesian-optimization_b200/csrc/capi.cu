@@ -438,6 +438,7 @@ int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value) {
   ENTER();
   SBO_REQUIRE(name != nullptr, "null option name");
   if (!strcmp(name, "posterior_variant")) { ctx->opt_posterior_variant = value; return SBO_OK; }
+  if (!strcmp(name, "posterior_tables")) { ctx->opt_posterior_tables = value; return SBO_OK; }
   if (!strcmp(name, "posterior_fused")) { ctx->opt_posterior_fused = value; return SBO_OK; }
   if (!strcmp(name, "posterior_chunk_mb")) { ctx->opt_posterior_chunk_mb = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_variant")) { ctx->opt_fantasy_variant = value; return SBO_OK; }

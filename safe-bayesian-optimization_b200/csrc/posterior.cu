@@ -695,8 +695,10 @@ int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v) {
   }
   SBO_CUDA(cudaMemsetAsync(ctx->lmax.p, 0, sizeof(double) * SBO_MAX_G, ctx->stream));
   ev_reset(ctx, 1); ev_reset(ctx, 2);
+  // meshgrids: the cross-covariance kernel takes its kernel values from the separable factor tables (d loads + d-1
+  // multiplies instead of an FP64 exp per entry) whether or not the solve is fused
   TabSpec ts{};
-  if (fused) {
+  if (ctx->gs.kind == 1 && (fused || ctx->opt_posterior_tables)) {
     ev_begin(ctx, 1);
     SBO_TRY(build_tables(ctx, &ts));
     ev_end(ctx);

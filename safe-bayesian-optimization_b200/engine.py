@@ -49,7 +49,8 @@ class GridEngine:
         import os
         for env, opt in (("SBO_FANTASY_VARIANT", "fantasy_variant"), ("SBO_POSTERIOR_VARIANT", "posterior_variant"),
                          ("SBO_FANTASY_GX", "fantasy_gx"), ("SBO_POSTERIOR_CHUNK_MB", "posterior_chunk_mb"),
-                         ("SBO_POSTERIOR_FUSED", "posterior_fused"), ("SBO_FANTASY_REFINE", "fantasy_refine")):
+                         ("SBO_POSTERIOR_FUSED", "posterior_fused"), ("SBO_FANTASY_REFINE", "fantasy_refine"),
+                         ("SBO_POSTERIOR_TABLES", "posterior_tables")):
             if os.environ.get(env):
                 self.set_option(opt, int(os.environ[env]))
 
