@@ -258,6 +258,7 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
  *   "prior_mean_zero"    1: zero prior mean for every GP at the next sbo_set_model (GP_Robust.py, StableOpt) | 0 (default) GP_Safe.py:331
  *   "fantasy_refine"     2 (default): the TF32 and TF32X3 fantasy expanders settle every pair inside their error bound in FP64
  *                        (the counts are the FP64 counts) | 1: TF32X3 only | 0: decide on the tensor-core value
+ *   "fantasy_refine_cap" > 0: initial capacity (pairs) of the ambiguous-pair list instead of the heuristic (test hook)
  *   "fantasy_f64_variant" 1 (default): FP64 fantasy expander on the FP64 tensor cores (DMMA tiles) | 0: SIMT reference kernel
  *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */
 int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value);

@@ -443,6 +443,7 @@ int sbo_set_option(sbo_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "posterior_chunk_mb")) { ctx->opt_posterior_chunk_mb = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_variant")) { ctx->opt_fantasy_variant = value; return SBO_OK; }
   if (!strcmp(name, "prior_mean_zero")) { ctx->opt_prior_mean_zero = value; return SBO_OK; }
+  if (!strcmp(name, "fantasy_refine_cap")) { ctx->opt_fantasy_refine_cap = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_refine")) { ctx->opt_fantasy_refine = value; return SBO_OK; }
   if (!strcmp(name, "fantasy_f64_variant")) { ctx->opt_fantasy_f64_variant = value; return SBO_OK; }
   if (!strcmp(name, "pair_cull")) { ctx->opt_pair_cull = value; return SBO_OK; }

@@ -187,6 +187,7 @@ struct sbo_ctx {
   int64_t opt_fantasy_f64_variant = 1; // FP64 fantasy expander: 1 (default) tensor cores (DMMA 128x64 tiles) | 0 SIMT reference kernel
   int64_t opt_fantasy_refine = 2;     // tensor-core fantasy expander: pairs the FP32/TF32 error bound cannot settle are re-evaluated in FP64 (exact
                                       // counts): 2 (default) TF32 and TF32X3, 1 TF32X3 only, 0 off (decide on the tensor-core value)
+  int64_t opt_fantasy_refine_cap = 0; // > 0: initial capacity of the ambiguous-pair list (tests force the overflow / re-run path with it)
   int64_t opt_pair_cull = 1;         // Lipschitz pair kernels: exact bounding-box culling of staged tiles
   int64_t opt_fantasy_gx = 0;        // 2-CTA kernel: x tile pairs per raster group (0 = default)
 };

@@ -1346,16 +1346,32 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
         // list capacity: a 256th of the pairs, between 1 M and 32 M entries (C4: ~1 M ambiguous pairs of 3e10)
         long long cap = nx * nz / 256;
         cap = cap < (1LL << 20) ? (1LL << 20) : (cap > (1LL << 25) ? (1LL << 25) : cap);
+        if (ctx->opt_fantasy_refine_cap > 0) cap = ctx->opt_fantasy_refine_cap;      // test hook: force the overflow path
         SBO_TRY(sbo_ensure(ctx, ctx->amb_list, sizeof(int2) * (size_t)cap));
         SBO_TRY(sbo_ensure(ctx, ctx->amb_ctr, 2 * sizeof(unsigned long long)));
         SBO_CUDA(cudaMemsetAsync(ctx->amb_ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
         pr.refine = 1; pr.amb_list = (int2*)ctx->amb_list.p; pr.amb_count = (unsigned long long*)ctx->amb_ctr.p;
-        pr.amb_cap = (long long)(ctx->amb_list.cap / sizeof(int2));
+        pr.amb_cap = ctx->opt_fantasy_refine_cap > 0 ? cap : (long long)(ctx->amb_list.cap / sizeof(int2));
       }
       SBO_TRY(fantasy_tc_run(ctx, fc, ps.precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p,
                              (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt, &pr));
       ps.pairs_evaluated = (ps.sorted ? run_pairs : nx * nz) * nc;
       if (refine) {
+        // the list was sized by a heuristic: if more pairs were ambiguous than it holds (the entries past the capacity were
+        // dropped, the counter kept counting), size it exactly and run the GEMM once more -- never refine a truncated list
+        unsigned long long n_amb = 0;
+        SBO_CUDA(cudaMemcpyAsync(&n_amb, ctx->amb_ctr.p, sizeof(n_amb), cudaMemcpyDeviceToHost, ctx->stream));
+        SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if ((long long)n_amb > pr.amb_cap) {
+          SBO_REQUIRE(n_amb < (1ULL << 31), "split/TF32 refinement: more than 2^31 ambiguous pairs on this shard (use fantasy_refine = 0 or fp64)");
+          SBO_TRY(sbo_ensure(ctx, ctx->amb_list, sizeof(int2) * (size_t)n_amb));
+          pr.amb_list = (int2*)ctx->amb_list.p; pr.amb_cap = (long long)(ctx->amb_list.cap / sizeof(int2));
+          SBO_CUDA(cudaMemsetAsync(ctx->amb_ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+          SBO_CUDA(cudaMemsetAsync(result_dev, 0, res_bytes, ctx->stream));
+          ev_end(ctx);
+          SBO_TRY(fantasy_tc_run(ctx, fc, ps.precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p,
+                                 (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt, &pr));
+        }
         ev_end(ctx);
         ev_begin(ctx, 7);
         SBO_TRY(refine_ambiguous(ctx, fc, nx, nz, cnt, row_perm));

@@ -69,3 +69,25 @@ def test_fp64_tensor_core_kernel_matches_the_simt_kernel(engine):
             assert dd.sum() <= 2, (d, k, int(dd.sum()))
             assert r["n_x"] == ref["n_x"] and r["n_z"] == ref["n_z"]
         print(f"fp64 dmma d={d} n={n}: newly-safe {int(ref['counts'].sum())}, pairs evaluated {res[(1, 1)]['pairs_evaluated']} of {ref['pairs_algorithmic']}")
+
+
+def test_refinement_list_overflow_reruns_with_an_exact_size(engine, oracle):
+    """The ambiguous-pair list of the refining tensor-core epilogue is sized by a heuristic; when it overflows the library
+    sizes it exactly and runs the GEMM once more.  Forced here with a 16-entry list: the counts must still be FP64's."""
+    from sbo_b200 import _capi as capi, workloads
+    ds, lo, hi, pts, beta = workloads.small(d=4, pts_per_dim=9, n=200, seed=11, G=4)
+    engine.set_model(ds)
+    engine.set_grid(lo, hi, pts)
+    res = {}
+    for prec in ("fp64", "tf32"):
+        p, kv = capi.PRECISIONS[prec]
+        engine.posterior(keep_v=kv, fetch=False)
+        engine.sets(beta, capi.UNSAFE_ANY)
+        try:
+            engine.set_option("fantasy_refine_cap", 16 if prec == "tf32" else 0)
+            res[prec] = engine.expander(beta, None, capi.MODE_FANTASY, p, want_counts=True)
+        finally:
+            engine.set_option("fantasy_refine_cap", 0)
+    assert res["tf32"]["n_ambiguous"] > 16, "the case must overflow a 16-entry list to test anything"
+    assert np.abs(res["tf32"]["counts"].astype(np.int64) - res["fp64"]["counts"]).sum() <= 1
+    assert res["tf32"]["best_idx"] == res["fp64"]["best_idx"]
