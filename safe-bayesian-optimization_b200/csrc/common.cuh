@@ -158,6 +158,7 @@ struct sbo_ctx {
   DevBuf imp_rows;
   DevBuf vx, vz, aux_x, aux_z;
   DevBuf pp_x, pp_m, pp_v, pp_k, pp_g;   // scratch of the arbitrary-point posterior calls
+  DevBuf tc_stats;                        // maxima behind the absolute error terms of the refining epilogue
   DevBuf tc_row, tc_col, tc_err;          // FP32 row/column records of the tcgen05 fantasy kernel
   DevBuf nll_K, nll_in;                   // batched NLL (hyper-parameter fit): P x npad x npad factors, inputs/outputs
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)

@@ -828,7 +828,8 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 template <int D4>
 __global__ void __launch_bounds__(256)
 k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, const double* __restrict__ coords,
-             const double* __restrict__ a, const double* __restrict__ b, float* __restrict__ rec, double esc) {
+             const double* __restrict__ a, const double* __restrict__ b, float* __restrict__ rec, double esc,
+             unsigned long long* __restrict__ stats) {
   constexpr int RS = 4 * D4 + 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
@@ -851,6 +852,21 @@ k_tc_records(FantasyConsts fc, long long n, long long npadrows, int is_row, cons
     o[k * st] = is_row ? (float)(2.0 * h * w * x) : (float)x;
   }
   const double av = a[(size_t)c * n + t], bv = b[(size_t)c * n + t];
+  if (stats) {   // maxima the host turns into the absolute error terms of the refining epilogue (non-negative doubles order like
+                 // integers); reduced over the active lanes of the warp first: one atomic per warp and statistic
+    const unsigned act = __activemask();
+    unsigned long long m0 = (unsigned long long)__double_as_longlong(q);                           // sum_k w_k x_k^2
+    unsigned long long m1 = is_row ? 0ULL : (unsigned long long)__double_as_longlong(fabs(av));     // |m_z|
+    unsigned long long m2 = is_row ? 0ULL : (unsigned long long)__double_as_longlong(fmax(bv, 0.0));   // sigma_z^2
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long a0 = __shfl_xor_sync(act, m0, o), a1 = __shfl_xor_sync(act, m1, o), a2 = __shfl_xor_sync(act, m2, o);
+      if ((act >> ((threadIdx.x & 31) ^ o)) & 1u) { m0 = max(m0, a0); m1 = max(m1, a1); m2 = max(m2, a2); }
+    }
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) {
+      atomicMax(stats + (is_row ? 0 : 1), m0);
+      if (!is_row) { atomicMax(stats + 2, m1); atomicMax(stats + 3, m2); }
+    }
+  }
   if (is_row) {
     o[4 * D4] = (float)(log2(fc.sf2[c]) - h * q);
     o[4 * D4 + 1] = (float)av;
@@ -1034,18 +1050,41 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   const double c1 = refine ? ((split ? 9.5367431640625e-07 : 9.7680091857910156e-04) + (fc.npad / 8) * 1.1920928955078125e-07) : 0.0;
   const double esc = refine ? sqrt(c1) : 0.0;
   tc::RefineArgs ra{};
-  if (refine) { ra.list = pr->amb_list; ra.count = pr->amb_count; ra.cap = pr->amb_cap; ra.e_abs = 2e-6f; ra.d_mu = 2e-6f; ra.d_t = 4e-6f; }
+  unsigned long long* stats = nullptr;
+  if (refine) {
+    ra.list = pr->amb_list; ra.count = pr->amb_count; ra.cap = pr->amb_cap;
+    SBO_TRY(sbo_ensure(ctx, ctx->tc_stats, 4 * sizeof(unsigned long long)));
+    stats = (unsigned long long*)ctx->tc_stats.p;
+    SBO_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  }
   ev_begin(ctx, 6);
   if (D4 == 1) {
-    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec, esc);
+    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec, esc, stats);
     SBO_LAUNCH_CHECK();
-    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec, esc);
+    tc::k_tc_records<1><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec, esc, stats);
     SBO_LAUNCH_CHECK();
   } else {
-    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec, esc);
+    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nxp, 256), nc), 256, 0, ctx->stream>>>(fc, nx, nxp, 1, xn, ax, bx, rowrec, esc, stats);
     SBO_LAUNCH_CHECK();
-    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec, esc);
+    tc::k_tc_records<2><<<dim3((unsigned)cdiv(nzp, 256), nc), 256, 0, ctx->stream>>>(fc, nz, nzp, 0, zn, mz, sz, colrec, esc, stats);
     SBO_LAUNCH_CHECK();
+  }
+  if (refine) {
+    // absolute error terms of the FP32 epilogue from the data (one small read-back):
+    //   exponent  e = (Cx - Bz) + sum xx_k z_k : 12*D4+3 roundings (inputs and FMAs) of magnitudes <= T = |log2 sf2| + 2h(Ax + Az),
+    //             k = ex2.approx(e) (2 ulp), cov = k - acc (1 rounding of <= 2 sf2)             -> e_abs
+    //   mean      mu' = cov*a + m : two roundings of <= |m|max + beta*sqrt(sf2) (a*|cov| <= beta*sigma_z)   -> d_mu
+    //   variance  t = s' - cov^2 b', compared with mu'^2 near mu'^2 ~ t <= beta^2 (s_z + sf2)     -> d_t
+    double st[4];
+    SBO_CUDA(cudaMemcpyAsync(st, stats, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+    double sf2max = 0.0, lsf = 0.0;
+    for (int c = 0; c < nc; ++c) { sf2max = fmax(sf2max, fc.sf2[c]); lsf = fmax(lsf, fabs(log2(fc.sf2[c]))); }
+    const double h = 0.5 * 1.4426950408889634, u = 5.9604644775390625e-08;           // u = 2^-24
+    const double T = lsf + 2.0 * h * (st[0] + st[1]);
+    ra.e_abs = (float)(sf2max * (0.6931471805599453 * u * (12 * D4 + 3) * T * 1.05 + 8.0 * u) + 4.0 * u * sf2max);
+    ra.d_mu = (float)(4.0 * u * (st[2] + fc.beta * sqrt(sf2max)) + 1e-9);
+    ra.d_t = (float)(8.0 * u * fc.beta * fc.beta * (st[3] + sf2max) + 1e-9);
   }
   int* err = (int*)ctx->tc_err.p;
   // variant: bit 0: BN = 256, bit 1: 8 epilogue warps, bit 2: 2-CTA pairs (cta_group::2, 256 x 256 tile pairs);
