@@ -134,6 +134,9 @@ int sbo_sets(sbo_ctx* ctx, double beta, int unsafe_rule, int strict, sbo_sets_re
 /* copy a bitmask of the local shard to the host: words[(count+31)/32] */
 int sbo_get_mask(sbo_ctx* ctx, int mask_kind, int which, uint32_t* words);
 int sbo_set_user_mask(sbo_ctx* ctx, const uint32_t* words);
+/* user mask = (mask_kind, e.g. SBO_MASK_SAFE; -1 = all points) AND the ball ||x - x0||_2 <= r, built on the device from the
+ * grid coordinates: the feasible set of GP_TR.BO.minimize_obj_lcb (models/GP_TR.py:43-54: safe set within the trust region) */
+int sbo_user_mask_ball(sbo_ctx* ctx, int mask_kind, const double* x0 /* d */, double r);
 /* device addresses for collectives on the caller's side (NCCL via torch.distributed) */
 int sbo_mask_dev(sbo_ctx* ctx, int mask_kind, int which, void** dev_ptr, int64_t* n_words);
 int sbo_posterior_dev(sbo_ctx* ctx, void** mean_dev, void** var_dev);

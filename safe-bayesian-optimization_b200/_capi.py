@@ -77,6 +77,7 @@ SIGNATURES = {
     "sbo_sets": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.POINTER(SetsResult)]),
     "sbo_get_mask": (C.c_int, [_P, C.c_int, C.c_int, _U32]),
     "sbo_set_user_mask": (C.c_int, [_P, _U32]),
+    "sbo_user_mask_ball": (C.c_int, [_P, C.c_int, _D, C.c_double]),
     "sbo_mask_dev": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I64]),
     "sbo_posterior_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "sbo_argreduce": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, _I64, _D]),

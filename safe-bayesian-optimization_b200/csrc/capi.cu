@@ -307,6 +307,11 @@ int sbo_set_user_mask(sbo_ctx* ctx, const uint32_t* words) {
   return SBO_OK;
 }
 
+int sbo_user_mask_ball(sbo_ctx* ctx, int mask_kind, const double* x0, double r) {
+  ENTER();
+  return ball_mask(ctx, mask_kind, x0, r);
+}
+
 int sbo_mask_dev(sbo_ctx* ctx, int mask_kind, int which, void** dev_ptr, int64_t* n_words) {
   ENTER();
   SBO_REQUIRE(dev_ptr && n_words, "null out pointer");

@@ -235,6 +235,7 @@ int model_upload(sbo_ctx* ctx, int n, int d, int G, const double* X_norm, const 
                  const double* X_mean, const double* X_std, const double* Y_mean, const double* Y_std,
                  const double* hyp);
 int model_append(sbo_ctx* ctx, const double* x_norm_new, const double* y_norm_new);
+int ball_mask(sbo_ctx* ctx, int mask_kind, const double* x0, double r);
 int stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value, int64_t* n_robust_safe, double* score_host);
 int nll_batch(sbo_ctx* ctx, int n, int d, const double* X_norm, const double* y, int P, const double* hyp, double* nll);
 int posterior_run(sbo_ctx* ctx, int with_grad, int keep_v);

@@ -595,6 +595,41 @@ int argreduce_run(sbo_ctx* ctx, int kind, const uint32_t* mask_dev, const double
   return SBO_OK;
 }
 
+// user mask = (mask_kind) AND ball ||x - x0||_2 <= r, built on the device from the implicit coordinates
+// (GP_TR.BO.minimize_obj_lcb, models/GP_TR.py:43-54 of the reference: the safe set inside the trust region)
+__global__ void __launch_bounds__(ST)
+k_ball_mask(GridSpec gs, const uint32_t* __restrict__ src, double x0, double x1, double x2, double x3, double x4, double x5,
+            double x6, double x7, double r, uint32_t* __restrict__ out) {
+  const long long p = (long long)blockIdx.x * ST + threadIdx.x;
+  bool in = false;
+  if (p < gs.count && (!src || ((src[p >> 5] >> (p & 31)) & 1u))) {
+    double x[SBO_MAX_D];
+    point_coords(gs, shard_global(gs, p), x);
+    const double c[SBO_MAX_D] = {x0, x1, x2, x3, x4, x5, x6, x7};
+    double s = 0.0;
+    for (int k = 0; k < gs.d; ++k) { const double df = __dsub_rn(x[k], c[k]); s = __dadd_rn(s, __dmul_rn(df, df)); }
+    in = sqrt(s) <= r;                                  // numpy.linalg.norm(x - x0) <= r, same operations
+  }
+  const uint32_t w = __ballot_sync(0xffffffffu, in);
+  if ((threadIdx.x & 31) == 0 && p < gs.count) out[p >> 5] = w;
+}
+int ball_mask(sbo_ctx* ctx, int mask_kind, const double* x0, double r) {
+  SBO_REQUIRE(ctx->have_grid && x0, "sbo_user_mask_ball: no grid");
+  const uint32_t* src = nullptr;
+  if (mask_kind >= 0) {
+    SBO_REQUIRE(ctx->have_sets, "sbo_user_mask_ball: no sets to intersect with");
+    src = mask_ptr(ctx, mask_kind, 0);
+    SBO_REQUIRE(src != nullptr, "mask not available");
+  }
+  SBO_TRY(sbo_ensure(ctx, ctx->m_user, sizeof(uint32_t) * mask_words(ctx)));
+  double c[SBO_MAX_D] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < ctx->gs.d; ++k) c[k] = x0[k];
+  k_ball_mask<<<(unsigned)cdiv(ctx->gs.count, ST), ST, 0, ctx->stream>>>(ctx->gs, src, c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], r,
+                                                                        (uint32_t*)ctx->m_user.p);
+  SBO_LAUNCH_CHECK();
+  return SBO_OK;
+}
+
 // StableOpt: robust safe set + min-max over the disturbance axes of the meshgrid (see k_stable_columns)
 int stable_minmax(sbo_ctx* ctx, int n_controlled, int fun_kind, double beta, int64_t* xc_idx, double* value, int64_t* n_robust_safe,
                   double* score_host) {

@@ -244,6 +244,11 @@ class GridEngine:
         w = np.ascontiguousarray(w)
         self._ck(self._lib.sbo_set_user_mask(self._h, w.ctypes.data_as(C.POINTER(C.c_uint32))))
 
+    def user_mask_ball(self, x0, r, mask_kind=capi.MASK_SAFE):
+        """user mask = mask_kind AND ||x - x0|| <= r, built on the device (sbo_user_mask_ball)."""
+        c = _f64(x0).reshape(-1)
+        self._ck(self._lib.sbo_user_mask_ball(self._h, int(mask_kind), capi.dptr(c), float(r)))
+
     def mask_dev(self, kind, which=0):
         p = C.c_void_p()
         n = C.c_int64()

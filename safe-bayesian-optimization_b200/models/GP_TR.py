@@ -38,8 +38,7 @@ class BO(_GridBO):
         """GP_TR.py:43-51 -- min lcb_0 over {lcb_i >= 0, i >= 1} within the ball (x_0, r) -> (x, value)."""
         self._ensure_step()
         capi = self._capi()
-        allowed = self.engine.mask(capi.MASK_SAFE) & self._ball_mask(x_0, r)
-        self.engine.set_user_mask(allowed)
+        self.engine.user_mask_ball(x_0, r, capi.MASK_SAFE)          # S AND ball, on the device (no mask round trip)
         idx, val = self.engine.argreduce(capi.ARGMIN_LCB0, capi.MASK_USER)
         if idx < 0:
             return self._x(-1), np.inf
