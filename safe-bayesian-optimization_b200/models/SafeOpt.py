@@ -9,7 +9,8 @@ expander pair kernel -> deterministic arg-reductions (lowest grid index on ties)
 Additive keyword arguments (defaults reproduce the reference's semantics):
   grid_points_per_dim  400 for d <= 2 (the reference's plot grid, test/test_SafeOpt.py:325-326)
   expander_mode        'lipschitz' (reference-exact pair test) | 'fantasy' (north_star GEMM expander)
-  precision            'fp64' | 'tf32' | 'tf32x3' (fantasy GEMM only)
+  precision            'fp64' | 'tf32' | 'tf32x3' (fantasy GEMM only; the tensor-core modes re-evaluate every pair inside their
+                       error bound in FP64, so all three return the FP64 counts)
   unsafe_rule          'all' (reference: lcb_constraint_min returns the MAX, SafeOpt.py:73-77) | 'any'
 """
 from __future__ import annotations
