@@ -93,7 +93,10 @@ static void reduce_arg(const std::vector<double>& g, int n, int nranks, int k, b
 }
 
 // the pair stage of one step on the sharded grid; `pr` gets GLOBAL optima (identical on every rank)
-static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, double beta, const double* L, sbo_pair_result* pr) {
+// s2 (optional): this rank's pass-2 result (minimiser); its reduction rides on the first gather of the pair stage and is
+// written to sets_out, so that a step needs three small all-gathers instead of five
+static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, double beta, const double* L, sbo_pair_result* pr,
+                         const sbo_sets_result* s2 = nullptr, sbo_sets_result* sets_out = nullptr) {
   sbo_comm* cm = ctx->comm;
   const int R = cm->nranks, rank = cm->rank;
   const int nc = ctx->ms.G - 1;
@@ -102,15 +105,23 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   SBO_TRY(pairs_prepare(ctx, mode, precision, beta, L, &info));
   // (1) candidate counts of every rank
   std::vector<double> g;
-  double mine1[2] = {(double)info.n_x_local, (double)info.n_z_local};
-  SBO_TRY(gather_record(ctx, mine1, 2, g));
+  double mine1[6] = {(double)info.n_x_local, (double)info.n_z_local, (double)mask_words(ctx),
+                     s2 ? s2->minimizer_var : 0.0, s2 ? (double)s2->minimizer_idx : -1.0, s2 ? (double)s2->n_min : 0.0};
+  SBO_TRY(gather_record(ctx, mine1, 6, g));
   std::vector<int64_t> n_all(R);
   int64_t n_total = 0, offset = 0, nz_total = 0;
+  long long wpr = 0;
   for (int r = 0; r < R; ++r) {
-    n_all[r] = (int64_t)g[2 * r];
+    n_all[r] = (int64_t)g[6 * r];
     if (r < rank) offset += n_all[r];
     n_total += n_all[r];
-    nz_total += (int64_t)g[2 * r + 1];
+    nz_total += (int64_t)g[6 * r + 1];
+    wpr = wpr > (long long)g[6 * r + 2] ? wpr : (long long)g[6 * r + 2];
+  }
+  if (s2 && sets_out) {
+    reduce_arg(g, 6, R, 3, true, &sets_out->minimizer_var, &sets_out->minimizer_idx);
+    sets_out->n_min = 0;
+    for (int r = 0; r < R; ++r) sets_out->n_min += (int64_t)g[6 * r + 5];
   }
   // (2) export into the gathered buffers, complete them with one grouped broadcast per rank
   const size_t row_b = sizeof(double) * (size_t)info.row_doubles, v_b = (size_t)info.vrow_bytes;
@@ -137,10 +148,6 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   if (!fantasy && R > 1) {
     SBO_TRY(pairs_set_segments(ctx, R, rank, n_all.data()));
     {   // SafeOpt expander: split by candidates; GoOSE target: split by (grid-ordered) unsafe tiles -- both over ALL unsafe points
-      double w1 = (double)mask_words(ctx);
-      SBO_TRY(gather_record(ctx, &w1, 1, g));
-      long long wpr = 0;
-      for (int r = 0; r < R; ++r) wpr = wpr > (long long)g[r] ? wpr : (long long)g[r];
       SBO_TRY(sbo_ensure(ctx, cm->masks, sizeof(uint32_t) * (size_t)wpr * (R + 1)));
       uint32_t* loc = (uint32_t*)cm->masks.p;
       uint32_t* all = loc + wpr;
@@ -198,7 +205,7 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
 }
 
 // posterior + both set passes on the sharded grid; fills the set part of `out`
-static int sharded_sets(sbo_ctx* ctx, double beta, int unsafe_rule, int with_grad, int keep_v, bool need_pass2, sbo_step_result* out) {
+static int sharded_sets(sbo_ctx* ctx, double beta, int unsafe_rule, int with_grad, int keep_v, sbo_sets_result* s2_local, sbo_step_result* out) {
   sbo_comm* cm = ctx->comm;
   const int R = cm->nranks, G = ctx->ms.G;
   SBO_TRY(posterior_run(ctx, with_grad, keep_v));
@@ -224,14 +231,7 @@ static int sharded_sets(sbo_ctx* ctx, double beta, int unsafe_rule, int with_gra
     for (int i = 0; i < G; ++i) out->L[i] = fmax(out->L[i], g[(size_t)r * n1 + 6 + i]);
   }
   out->sets.minimizer_var = -INFINITY; out->sets.minimizer_idx = -1;
-  if (need_pass2) {
-    sbo_sets_result s2;
-    SBO_TRY(sets_pass2(ctx, out->sets.min_ucb0, &s2));
-    double m2[3] = {s2.minimizer_var, (double)s2.minimizer_idx, (double)s2.n_min};
-    SBO_TRY(gather_record(ctx, m2, 3, g));
-    reduce_arg(g, 3, R, 0, true, &out->sets.minimizer_var, &out->sets.minimizer_idx);
-    for (int r = 0; r < R; ++r) out->sets.n_min += (int64_t)g[(size_t)r * 3 + 2];
-  }
+  if (s2_local) SBO_TRY(sets_pass2(ctx, out->sets.min_ucb0, s2_local));     // reduced with the first gather of the pair stage
   return SBO_OK;
 }
 
@@ -284,10 +284,11 @@ int sbo_safeopt_step_sharded(sbo_ctx* ctx, double beta, int mode, int precision,
   const int G = ctx->ms.G;
   const bool fantasy = mode == SBO_MODE_FANTASY;
   const int keep_v = fantasy ? (precision == SBO_PREC_FP64 ? 1 : (precision == SBO_PREC_TF32 ? 2 : 3)) : 0;
-  SBO_TRY(sharded_sets(ctx, beta, unsafe_rule, (!fantasy && !L) ? 1 : 0, keep_v, true, out));
+  sbo_sets_result s2;
+  SBO_TRY(sharded_sets(ctx, beta, unsafe_rule, (!fantasy && !L) ? 1 : 0, keep_v, &s2, out));
   double Lg[SBO_MAX_G];
   for (int i = 0; i < SBO_MAX_G; ++i) Lg[i] = L ? (i < G ? L[i] : 0.0) : out->L[G - 1];   // SafeOpt.py:110: L of constraint n_fun-1
-  SBO_TRY(sharded_pairs(ctx, mode, fantasy ? precision : SBO_PREC_FP64, false, beta, fantasy ? nullptr : Lg, &out->pairs));
+  SBO_TRY(sharded_pairs(ctx, mode, fantasy ? precision : SBO_PREC_FP64, false, beta, fantasy ? nullptr : Lg, &out->pairs, &s2, &out->sets));
   const double std_min = out->sets.minimizer_idx >= 0 ? sqrt(out->sets.minimizer_var) : 0.0;
   const double std_exp = out->pairs.best_idx >= 0 ? sqrt(out->pairs.best_value) : 0.0;
   out->x_new_idx = std_min > std_exp ? out->sets.minimizer_idx : out->pairs.best_idx;   // test_SafeOpt.py:153-158
@@ -302,7 +303,7 @@ int sbo_goose_step_sharded(sbo_ctx* ctx, double beta, int unsafe_rule, const dou
   SBO_REQUIRE(out != nullptr, "null result");
   memset(out, 0, sizeof(*out));
   const int G = ctx->ms.G;
-  SBO_TRY(sharded_sets(ctx, beta, unsafe_rule, L ? 0 : 1, 0, false, out));
+  SBO_TRY(sharded_sets(ctx, beta, unsafe_rule, L ? 0 : 1, 0, nullptr, out));
   double Lg[SBO_MAX_G];
   for (int i = 0; i < SBO_MAX_G; ++i) Lg[i] = L ? (i < G ? L[i] : 0.0) : out->L[G - 1];   // GoOSE.py:100
   SBO_TRY(sharded_pairs(ctx, SBO_MODE_LIPSCHITZ, SBO_PREC_FP64, true, beta, Lg, &out->pairs));
