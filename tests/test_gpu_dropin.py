@@ -341,3 +341,31 @@ def test_lipschitz_needs_a_posterior_with_gradients(engine):
         engine.lipschitz()
     engine.posterior(with_grad=True, fetch=False)
     assert np.all(engine.lipschitz()[1:] > 0)
+
+
+def test_library_communicator_single_rank_steps_match_the_plain_steps():
+    """csrc/comm.cu on one GPU: a 1-rank NCCL communicator (sbo_comm_unique_id / sbo_comm_init) and the whole sharded steps
+    (sbo_safeopt_step_sharded / sbo_goose_step_sharded) must return what GridEngine.safeopt_step / goose_step return.
+    (The 2-GPU agreement tests need a 2-GPU box; this one runs wherever the GPU suite runs.)"""
+    import sbo_b200
+    from sbo_b200 import _capi as capi, workloads
+    ds, lo, hi, pts, beta = workloads.small(d=4, pts_per_dim=9, n=200, seed=11, G=4)
+    eng = sbo_b200.GridEngine(0)
+    try:
+        eng.set_grid(lo, hi, pts)
+        eng.set_shard_cyclic(0, 1, 256)
+        eng.comm_init(0, 1, eng.comm_unique_id())
+        for mode, prec in (("fantasy", "tf32"), ("fantasy", "fp64"), ("lipschitz", "fp64")):
+            a = eng.safeopt_step(ds, beta, mode=mode, precision=prec, unsafe_rule=capi.UNSAFE_ANY)
+            b = eng.safeopt_step_sharded(ds, beta, mode=mode, precision=prec, unsafe_rule=capi.UNSAFE_ANY)
+            for k in ("n_safe", "n_unsafe", "n_min", "min_ucb0_idx", "minimizer_idx", "expander_idx", "x_new_idx"):
+                assert a[k] == b[k], (mode, prec, k)
+            assert a["expander"]["n_hit"] == b["expander"]["n_hit"] and a["expander"]["n_z"] == b["expander"]["n_z"]
+            assert a["min_ucb0"] == b["min_ucb0"] and a["minimizer_var"] == b["minimizer_var"]
+        a = eng.goose_step(ds, beta, unsafe_rule=capi.UNSAFE_ANY)
+        b = eng.goose_step_sharded(ds, beta, unsafe_rule=capi.UNSAFE_ANY)
+        for k in ("n_safe", "n_unsafe", "min_lcb0_idx", "target_idx", "x_new_idx", "explore_idx"):
+            assert a[k] == b[k], k
+        assert a["target_lcb"] == b["target_lcb"]
+    finally:
+        eng.close()
