@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SBO_BENCH_PRECISION", "tf32"),
                     help="fantasy GEMM operands: tf32 (default: single TF32 pass; every pair inside its error bound is re-evaluated in FP64, "
                          "so the counts are the FP64 counts), tf32x3 (split TF32, same refinement with a 100x narrower band), fp64 (DMMA)")
-    ap.add_argument("--refine", type=int, default=2, help="FP64 refinement of the tensor-core modes: 2 (library default) tf32 and tf32x3, 1 tf32x3 only, 0 off")
+    ap.add_argument("--refine", type=int, default=2, help="FP64 refinement of the tensor-core modes: 2 (library default) tf32 and tf32x3, 1 tf32x3 only, 0 off, 3 bounds mode (classify only)")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end repetitions (default max(2, steps); the first is dropped when > 1)")
     ap.add_argument("--orchestrator", default="library", choices=["library", "torch"],
                     help="multi-GPU: collectives inside libsbo_b200 (sbo_comm_init, default) or issued by sharded.py through torch.distributed")
@@ -80,34 +80,51 @@ class Clocks:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []                     # (arrival time, fields)
         self.proc = None
+        self.t0 = None
 
     def start(self):
+        """Launch the sampler (before the warm-up steps: nvidia-smi needs a few hundred ms to deliver its first row, more than a
+        whole timed region at 8 GPUs)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Start of the timed region: only rows that arrive from here on are used (waits, bounded, for the sampler's first row)."""
+        t = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t < 2.0:
+            time.sleep(0.01)
+        self.t0 = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t1 = time.perf_counter()
+        time.sleep(0.12)                   # a row that was sampled inside the region may still be in the pipe
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.06]
+        window = "timed region"
+        if not inside and self.rows:       # region shorter than the sampling period: the rows next to it (warm-up steps run right before)
+            inside = [r for _, r in self.rows[-2:]]
+            window = "nearest samples (timed region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -116,7 +133,7 @@ class Clocks:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------
@@ -285,13 +302,16 @@ def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
     from sbo_b200 import workloads, sharded
     ds5, lo5, hi5, pts5, beta5 = workloads.c5()
     n5, d5 = ds5["X_norm"].shape
-    out = {"workload": "C5: synthetic step, d=6, N=16^6=2^24 grid, n=2048, G=4 (3 constraints)", "precision": "tf32", "refine": 0, "n_gpus": world}
+    out = {"workload": "C5: synthetic step, d=6, N=16^6=2^24 grid, n=2048, G=4 (3 constraints)", "precision": "tf32", "refine": "3 (bounds)", "n_gpus": world}
     try:
         eng.release(3)
         torch.cuda.empty_cache()
-        # tensor-core decisions at this size: the TF32 band holds ~3e8 pairs per rank here and their FP64 re-evaluation at
-        # n = 2048 would gather ~30 TB of rows per rank (the refinement list is bounded at 32 M pairs)
-        eng.set_option("fantasy_refine", 0)
+        # bounds mode at this size: the TF32 band holds ~3e8 pairs per rank here and their FP64 re-evaluation at n = 2048 would
+        # gather ~30 TB of rows per rank, so the refining epilogue only CLASSIFIES -- the expander set is reported as the
+        # candidates with a pair settled newly safe (certified members of the FP64 set) plus the count of undecided ones
+        eng.set_option("fantasy_refine", 3 if (world == 1 or getattr(eng, "comm_ready", False)) else 0)
+        if not (world == 1 or getattr(eng, "comm_ready", False)):
+            out["refine"] = 0
         eng.set_grid(lo5, hi5, pts5)
         if world > 1:
             eng.set_shard_cyclic(rank, world, 256)
@@ -340,6 +360,11 @@ def c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier):
         out.update({"ms_per_step": ms, "value": pairs5 / (ms * 1e-3), "unit": "pair-evals/s", "pairs": pairs5, "pairs_evaluated": ev5,
                     "n_safe": int(r5["n_safe"]), "n_unsafe": int(r5["n_unsafe"]), "n_min": int(r5["n_min"]), "n_hit": int(ex5["n_hit"]),
                     "x_new_idx": int(r5["x_new_idx"]), "phase_ms_rank0": ph,
+                    "expander_bounds": {"certified_members": int(ex5["n_hit"]), "undecided_candidates": int(ex5.get("n_undecided", 0)),
+                                        "pairs_inside_error_bound": int(ex5.get("n_ambiguous", 0)),
+                                        "x_new_certified": bool(int(ex5.get("n_undecided", 0)) == 0 or
+                                                                ex5.get("undecided_best_value", -np.inf) < max(ex5["best_value"], r5["minimizer_var"])),
+                                        "note": "FP64 expander set = certified members + a subset of the undecided candidates"},
                     "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if ach else None,
                                  "kernel": "tc::k_fantasy_tc2 (tf32), per GPU, evaluated pairs only"},
                     "device_mem_high_water_gb": eng.mem_peak() / 2 ** 30,
@@ -417,12 +442,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-timed steps (value) ----
+    clocks = Clocks(local)
+    clocks.start()
     for _ in range(args.warmup):
         step()
     eng.kernel_launches(reset=True)
-    clocks = Clocks(local)
     barrier()
-    clocks.start()
+    clocks.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     phases = []
     res = None
@@ -488,6 +514,7 @@ def run_ours(args):
     c5 = None
     if (args.c5 == 1 or (args.c5 < 0 and world == 8)) and args.workload == "c4":
         c5 = c5_key(args, eng, torch, dist, stream, rank, world, dev, barrier)
+        eng.set_option("fantasy_refine", int(args.refine))
         eng.set_grid(lo, hi, pts)
         if world > 1:
             eng.set_shard_cyclic(rank, world, 256)
@@ -546,7 +573,7 @@ def run_ours(args):
             "config": {"workload": wl_name, "mode": args.mode, "precision": args.precision, "N": N, "n": n, "d": d, "G": G,
                        "beta": beta, "n_safe": int(res["n_safe"]), "n_unsafe": int(res["n_unsafe"]), "n_min": int(res["n_min"]),
                        "pairs": pairs, "pairs_evaluated": int(ex["pairs_evaluated"]), "n_hit": int(ex["n_hit"]), "x_new_idx": int(res["x_new_idx"]),
-                       "prune": int(args.prune), "refine": int(args.refine), "refined_pairs_fp64": int(ex.get("n_ambiguous", 0)), "refined_safe": int(ex.get("n_refined_safe", 0)),
+                       "prune": int(args.prune), "refine": int(args.refine), "refined_pairs_fp64": int(ex.get("n_ambiguous", 0)), "refined_safe": int(ex.get("n_refined_safe", 0)), "n_undecided": int(ex.get("n_undecided", 0)),
                        "value_counts": "all |S|*|Z|*(G-1) pairs: the exact pruning decides the skipped ones without evaluating them",
                        "l2": "256 MiB flush buffer written between timed steps; working set >> L2",
                        "excludes": "plant evaluation and hyper-parameter fit (host side in the reference too)"},

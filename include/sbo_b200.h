@@ -170,7 +170,12 @@ typedef struct sbo_pair_result {
   int64_t pairs_algorithmic;                     /* n_x * n_z * (constraints)         */
   int64_t pairs_evaluated;                       /* after tile-level early exit       */
   int64_t n_hit;                                 /* |expander set| (union over idx) or |target set| */
-  int64_t n_ambiguous, n_refined_safe;           /* fantasy TF32X3: pairs re-evaluated in FP64 / of those, newly safe (local shard) */
+  int64_t n_ambiguous, n_refined_safe;           /* fantasy TF32/TF32X3: pairs inside the error bound (re-evaluated in FP64 unless bounds mode) / of those, newly safe */
+  /* bounds mode ("fantasy_refine" = 3): n_hit counts the candidates with at least one pair SETTLED newly safe (certified members of the
+   * FP64 expander set); n_undecided the candidates with no settled pair but at least one pair inside the error bound (the FP64 set is
+   * the certified set plus a subset of these); undecided_best_* = argmax var_0 over them (-1 if none).  The reported x_new (best_idx)
+   * equals the FP64 one whenever undecided_best_value < best_value.  counts[] then holds the settled counts, -1 for undecided candidates. */
+  int64_t n_undecided, undecided_best_idx; double undecided_best_value;
 } sbo_pair_result;
 int sbo_expander(sbo_ctx* ctx, int mode, int precision, double beta, const double* L /* G, lipschitz mode */,
                  sbo_pair_result* out, int32_t* counts /* count, fantasy mode, or NULL */);
@@ -261,6 +266,9 @@ int sbo_phase_ms(sbo_ctx* ctx, int phase, double* ms);
  *   "prior_mean_zero"    1: zero prior mean for every GP at the next sbo_set_model (GP_Robust.py, StableOpt) | 0 (default) GP_Safe.py:331
  *   "fantasy_refine"     2 (default): the TF32 and TF32X3 fantasy expanders settle every pair inside their error bound in FP64
  *                        (the counts are the FP64 counts) | 1: TF32X3 only | 0: decide on the tensor-core value
+ *                        | 3: bounds mode -- no FP64 pass: the counts are the pairs the error bound settles as newly safe (a lower bound
+ *                        of the FP64 counts) and sbo_pair_result.n_undecided / undecided_best_* say what is left open (for shards
+ *                        whose ambiguous pairs do not fit a list: C5)
  *   "fantasy_refine_cap" > 0: initial capacity (pairs) of the ambiguous-pair list instead of the heuristic (test hook)
  *   "fantasy_f64_variant" 1 (default): FP64 fantasy expander on the FP64 tensor cores (DMMA tiles) | 0: SIMT reference kernel
  *   "pair_cull"          1 (default): exact bounding-box tile culling in the Lipschitz pair kernels | 0 all pairs */

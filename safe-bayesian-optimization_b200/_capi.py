@@ -36,7 +36,8 @@ class PairResult(C.Structure):
                 ("per_idx", C.c_int64 * MAX_G), ("per_value", C.c_double * MAX_G),
                 ("n_x", C.c_int64), ("n_z", C.c_int64),
                 ("pairs_algorithmic", C.c_int64), ("pairs_evaluated", C.c_int64), ("n_hit", C.c_int64),
-                ("n_ambiguous", C.c_int64), ("n_refined_safe", C.c_int64)]
+                ("n_ambiguous", C.c_int64), ("n_refined_safe", C.c_int64),
+                ("n_undecided", C.c_int64), ("undecided_best_idx", C.c_int64), ("undecided_best_value", C.c_double)]
 
 
 class StepResult(C.Structure):

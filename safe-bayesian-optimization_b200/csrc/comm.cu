@@ -166,7 +166,11 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   SBO_TRY(sbo_ensure(ctx, cm->result, (res_b ? res_b : 16) + (goose_global ? (size_t)nc * info.n_z_local + 16 : 0)));
   SBO_TRY(pairs_run(ctx, goose ? 1 : 0, cm->result.p));
   if (!goose && n_total > 0) {
-    if (fantasy) SBO_NCCL(g_nccl.AllReduce(cm->result.p, cm->result.p, (size_t)n_total, ncclInt32, ncclSum, NC(ctx), ctx->stream));
+    if (fantasy) {
+      SBO_NCCL(g_nccl.AllReduce(cm->result.p, cm->result.p, (size_t)n_total, ncclInt32, ncclSum, NC(ctx), ctx->stream));
+      if (ctx->ps.bounds)    // bounds mode: the per-candidate undecided-pair counts are combined like the settled counts
+        SBO_NCCL(g_nccl.AllReduce(ctx->amb_rows.p, ctx->amb_rows.p, (size_t)n_total, ncclInt32, ncclSum, NC(ctx), ctx->stream));
+    }
     else SBO_NCCL(g_nccl.AllReduce(cm->result.p, cm->result.p, (size_t)nc * n_total, ncclUint8, ncclMax, NC(ctx), ctx->stream));
   }
   const void* res_ptr = cm->result.p;
@@ -180,11 +184,13 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
   SBO_TRY(pairs_finish(ctx, goose ? 1 : 0, goose ? 0 : offset, res_ptr, &loc, nullptr));
   // (5) global optima: per constraint (value, index), then the first best over the constraints (SafeOpt.py:120-122)
   const int nmask = fantasy ? 1 : nc;
-  const int nrec = 2 * SBO_MAX_G + 4;
-  double mine2[2 * SBO_MAX_G + 4];
+  const int nrec = 2 * SBO_MAX_G + 8;
+  double mine2[2 * SBO_MAX_G + 8];
   for (int c = 0; c < SBO_MAX_G; ++c) { mine2[2 * c] = loc.per_value[c]; mine2[2 * c + 1] = (double)loc.per_idx[c]; }
   mine2[2 * SBO_MAX_G] = (double)loc.n_hit; mine2[2 * SBO_MAX_G + 1] = (double)loc.pairs_evaluated;
   mine2[2 * SBO_MAX_G + 2] = (double)loc.n_ambiguous; mine2[2 * SBO_MAX_G + 3] = (double)loc.n_refined_safe;
+  mine2[2 * SBO_MAX_G + 4] = loc.undecided_best_value; mine2[2 * SBO_MAX_G + 5] = (double)loc.undecided_best_idx;
+  mine2[2 * SBO_MAX_G + 6] = (double)loc.n_undecided; mine2[2 * SBO_MAX_G + 7] = 0.0;
   SBO_TRY(gather_record(ctx, mine2, nrec, g));
   memset(pr, 0, sizeof(*pr));
   pr->best_idx = -1; pr->best_value = goose ? INFINITY : -INFINITY;
@@ -199,6 +205,8 @@ static int sharded_pairs(sbo_ctx* ctx, int mode, int precision, bool goose, doub
     pr->n_hit += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G]; pr->pairs_evaluated += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 1];
     pr->n_ambiguous += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 2]; pr->n_refined_safe += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 3];
   }
+  reduce_arg(g, nrec, R, 2 * SBO_MAX_G + 4, true, &pr->undecided_best_value, &pr->undecided_best_idx);
+  for (int r = 0; r < R; ++r) pr->n_undecided += (int64_t)g[(size_t)r * nrec + 2 * SBO_MAX_G + 6];
   pr->n_x = n_total; pr->n_z = nz_total; pr->pairs_algorithmic = n_total * nz_total * nc;
   if (big) SBO_TRY(sbo_release(ctx, 2));
   return SBO_OK;

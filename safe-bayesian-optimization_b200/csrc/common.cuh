@@ -120,6 +120,7 @@ struct PairStage {
   long long seg_off[65] = {0};
   bool canon = false;
   long long nz_global = -1;
+  bool bounds = false;                               // fantasy_refine = 3: counts are settled lower bounds, amb_rows the undecided pairs
   long long n_ambiguous = 0, n_refined_safe = 0;     // split-TF32 refinement statistics of the last run
 };
 
@@ -164,7 +165,7 @@ struct sbo_ctx {
   DevBuf tile_bb;                         // bounding boxes of the staged tiles (Lipschitz pair kernels)
   DevBuf exp_rows, exp_v;                 // single-GPU export buffers of the staged pair driver
   DevBuf key_x, key_z, perm_x, perm_z, sort_ws, tile_keys, item_mask, item_list;   // exact pruning of the fantasy expander
-  DevBuf amb_list, amb_ctr, amb_mask, amb_xd, amb_zd, amb_rx, amb_rz, amb_pts, amb_vx, amb_vz;   // FP64 refinement of the split-TF32 expander
+  DevBuf amb_list, amb_ctr, amb_mask, amb_xd, amb_zd, amb_rx, amb_rz, amb_pts, amb_vx, amb_vz, amb_rows, m_und;   // FP64 refinement of the split-TF32 expander
   DevBuf st_score, st_mask;               // StableOpt: per-x_c worst-case score and robust-safe bitmask
   DevBuf gz_mask, gz_idx, gz_pay;         // all-gathered unsafe set of a sharded Lipschitz expander
   PairStage ps;

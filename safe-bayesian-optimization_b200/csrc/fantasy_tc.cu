@@ -47,6 +47,7 @@ struct Params {
   int2* amb_list;
   unsigned long long* amb_count;   // [0] entries appended (may exceed the capacity: overflow is detected by the host)
   long long amb_cap;
+  int* amb_rows;                   // bounds mode (fantasy_refine = 3): per-candidate number of ambiguous pairs, no list
   float e_abs, d_mu, d_t;          // absolute error terms of the FP32 epilogue (covariance, mean, variance side)
 };
 
@@ -796,6 +797,7 @@ k_fantasy_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (amb) {
             const int n = __popc(amb);
             const unsigned long long base = atomicAdd(p.amb_count, (unsigned long long)n);
+            if (p.amb_rows) { atomicAdd(p.amb_rows + (p.row_perm ? p.row_perm[xrow] : xrow), n); continue; }
             const int zc0 = zt * BN + (half * NCH + h) * 32;
             unsigned long long w = base;
             while (amb) {
@@ -936,7 +938,7 @@ static int launch(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx
   return SBO_OK;
 }
 
-struct RefineArgs { int2* list; unsigned long long* count; long long cap; float e_abs, d_mu, d_t; };
+struct RefineArgs { int2* list; unsigned long long* count; long long cap; float e_abs, d_mu, d_t; int* rows; };
 
 template <int D4, int EW, bool REFINE>
 static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp, long long nzp,
@@ -960,7 +962,7 @@ static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   p.rowrec = rowrec; p.colrec = colrec; p.counts = counts; p.err = err;
   p.sched_counter = (unsigned int*)(err + 1);
   p.item_list = item_list; p.row_perm = row_perm;
-  p.amb_list = ra.list; p.amb_count = ra.count; p.amb_cap = ra.cap; p.e_abs = ra.e_abs; p.d_mu = ra.d_mu; p.d_t = ra.d_t;
+  p.amb_list = ra.list; p.amb_count = ra.count; p.amb_cap = ra.cap; p.amb_rows = ra.rows; p.e_abs = ra.e_abs; p.d_mu = ra.d_mu; p.d_t = ra.d_t;
   if (p.n_items == 0) return SBO_OK;
   SBO_CUDA((cudaFuncSetAttribute(k_fantasy_tc2<D4, EW, REFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)));
   const int grid = 2 * (int)((p.n_items < clusters) ? p.n_items : clusters);
@@ -973,7 +975,7 @@ static int launch2(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
 
 // keys of the exact pruning (pairs.cu): sorted key_x[nx] (max side), key_z[nz] (min side), slot -> counts row
 struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run;
-                          int refine; int2* amb_list; unsigned long long* amb_count; long long amb_cap; };
+                          int refine; int2* amb_list; unsigned long long* amb_count; long long amb_cap; int* amb_rows; };
 // per tile of `tile` consecutive sorted entries: max (x side) or min (z side) of the keys
 __global__ void __launch_bounds__(256)
 k_tile_keys(long long n, int tile, int want_max, const double* __restrict__ key, double* __restrict__ out) {
@@ -1052,7 +1054,7 @@ int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long n
   tc::RefineArgs ra{};
   unsigned long long* stats = nullptr;
   if (refine) {
-    ra.list = pr->amb_list; ra.count = pr->amb_count; ra.cap = pr->amb_cap;
+    ra.list = pr->amb_list; ra.count = pr->amb_count; ra.cap = pr->amb_cap; ra.rows = pr->amb_rows;
     SBO_TRY(sbo_ensure(ctx, ctx->tc_stats, 4 * sizeof(unsigned long long)));
     stats = (unsigned long long*)ctx->tc_stats.p;
     SBO_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), ctx->stream));

@@ -590,6 +590,17 @@ k_counts_scatter(long long n, long long offset, const long long* __restrict__ id
   if (cnt_pt) cnt_pt[p] = c;
   if (c > 0) atomicOr(mask + (p >> 5), 1u << (p & 31));
 }
+// bounds mode: candidates the error bound leaves undecided (no settled newly-safe pair, at least one ambiguous pair)
+__global__ void __launch_bounds__(256)
+k_undecided_mask(long long n, long long offset, const long long* __restrict__ idx, const int* __restrict__ cnt_c,
+                 const int* __restrict__ amb_c, int* __restrict__ cnt_pt, uint32_t* __restrict__ mask) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (cnt_c[offset + t] > 0 || amb_c[offset + t] == 0) return;
+  const long long p = idx[t];
+  if (cnt_pt) cnt_pt[p] = -1;
+  atomicOr(mask + (p >> 5), 1u << (p & 31));
+}
 __global__ void __launch_bounds__(256)
 k_union_count(int nc, const uint32_t* __restrict__ masks, long long nwords, unsigned long long* __restrict__ out) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -883,7 +894,7 @@ int fantasy_build_items(sbo_ctx* ctx, long long nx, long long nz, int tile_x, in
                         const double* key_z, const long long** item_list, long long* n_list);
 
 struct FantasyPruneArgs { const double* key_x; const double* key_z; const int* row_perm; long long* items_run;
-                          int refine; int2* amb_list; unsigned long long* amb_count; long long amb_cap; };
+                          int refine; int2* amb_list; unsigned long long* amb_count; long long amb_cap; int* amb_rows; };
 int fantasy_tc_run(sbo_ctx* ctx, const FantasyConsts& fc, int split, long long nx, long long nz, long long nxp,
                    long long nzp, const float* Vx, const float* Vz, const double* aux_x, const double* aux_z, int* counts_c,
                    const FantasyPruneArgs* pr);
@@ -1250,6 +1261,7 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
   const long long nx = ps.nx_total, nz = ps.nz_local;
   ps.pairs_evaluated = 0;
   ps.counted = false;
+  ps.bounds = false;
   if (nc == 0) return SBO_OK;
   const size_t res_bytes = (ps.mode == SBO_MODE_FANTASY) ? sizeof(int) * (size_t)nx
                                                          : (size_t)nc * (goose ? (ps.nz_global >= 0 ? ps.nz_global : nz) : nx);
@@ -1342,7 +1354,18 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
       long long run_pairs = nx * nz;
       FantasyPruneArgs pr{key_x, key_z, row_perm, &run_pairs, 0, nullptr, nullptr, 0};
       const bool refine = (ps.precision == SBO_PREC_TF32X3 && ctx->opt_fantasy_refine >= 1) || (ps.precision == SBO_PREC_TF32 && ctx->opt_fantasy_refine >= 2);
-      if (refine) {
+      const bool bounds = refine && ctx->opt_fantasy_refine == 3;
+      ps.bounds = bounds; ps.n_ambiguous = 0; ps.n_refined_safe = 0;
+      if (bounds) {
+        // bounds mode: no list and no FP64 pass.  counts = the pairs the error bound SETTLES as newly safe (a lower bound of the
+        // FP64 counts), amb_rows = per candidate the number of pairs it cannot settle (counts + amb_rows is an upper bound)
+        SBO_TRY(sbo_ensure(ctx, ctx->amb_rows, sizeof(int) * (size_t)nx));
+        SBO_CUDA(cudaMemsetAsync(ctx->amb_rows.p, 0, sizeof(int) * (size_t)nx, ctx->stream));
+        SBO_TRY(sbo_ensure(ctx, ctx->amb_ctr, 2 * sizeof(unsigned long long)));
+        SBO_CUDA(cudaMemsetAsync(ctx->amb_ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        pr.refine = 1; pr.amb_list = nullptr; pr.amb_cap = 0; pr.amb_count = (unsigned long long*)ctx->amb_ctr.p;
+        pr.amb_rows = (int*)ctx->amb_rows.p;
+      } else if (refine) {
         // list capacity: a 256th of the pairs, between 1 M and 32 M entries (C4: ~1 M ambiguous pairs of 3e10)
         long long cap = nx * nz / 256;
         cap = cap < (1LL << 20) ? (1LL << 20) : (cap > (1LL << 25) ? (1LL << 25) : cap);
@@ -1356,7 +1379,12 @@ int pairs_run(sbo_ctx* ctx, int goose, void* result_dev) {
       SBO_TRY(fantasy_tc_run(ctx, fc, ps.precision == SBO_PREC_TF32X3 ? 1 : 0, nx, nz, nxp, nzp, (const float*)ctx->vx.p,
                              (const float*)ctx->vz.p, (const double*)ctx->aux_x.p, (const double*)ctx->aux_z.p, cnt, &pr));
       ps.pairs_evaluated = (ps.sorted ? run_pairs : nx * nz) * nc;
-      if (refine) {
+      if (bounds) {
+        unsigned long long n_amb = 0;
+        SBO_CUDA(cudaMemcpyAsync(&n_amb, ctx->amb_ctr.p, sizeof(n_amb), cudaMemcpyDeviceToHost, ctx->stream));
+        SBO_CUDA(cudaStreamSynchronize(ctx->stream));
+        ps.n_ambiguous = (long long)n_amb;
+      } else if (refine) {
         // the list was sized by a heuristic: if more pairs were ambiguous than it holds (the entries past the capacity were
         // dropped, the counter kept counting), size it exactly and run the GEMM once more -- never refine a truncated list
         unsigned long long n_amb = 0;
@@ -1410,7 +1438,9 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
   }
   unsigned long long h[2] = {0, 0};
   const long long nloc = goose ? nz : nx;
-  const bool have = nc > 0 && nloc > 0 && nxt > 0 && (nz > 0 || (!goose && ps.nz_global > 0)) && result_dev != nullptr;
+  const bool have = nc > 0 && nloc > 0 && nxt > 0 && (fantasy || nz > 0 || (!goose && ps.nz_global > 0)) && result_dev != nullptr;
+  const bool bounds = fantasy && ps.bounds && have;
+  unsigned long long h_und = 0;
   if (have) {
     ev_begin(ctx, 6);
     const long long* idx = (const long long*)(goose ? ctx->zs_idx.p : ctx->xs_idx.p);
@@ -1424,8 +1454,20 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
     SBO_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
     k_union_count<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(nmask, (const uint32_t*)mbuf.p, nw, ctr + 1);
     SBO_LAUNCH_CHECK();
-    ev_end(ctx);
     SBO_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bounds) {
+      // amb_rows holds the (all-reduced, sbo_*_step_sharded) per-candidate ambiguous-pair counts in the layout of result_dev
+      SBO_TRY(sbo_ensure(ctx, ctx->m_und, sizeof(uint32_t) * (size_t)nw));
+      SBO_CUDA(cudaMemsetAsync(ctx->m_und.p, 0, sizeof(uint32_t) * (size_t)nw, ctx->stream));
+      k_undecided_mask<<<(unsigned)cdiv(nx, 256), 256, 0, ctx->stream>>>(nx, offset, idx, (const int*)result_dev, (const int*)ctx->amb_rows.p,
+                                                                          (int*)ctx->counts.p, (uint32_t*)ctx->m_und.p);
+      SBO_LAUNCH_CHECK();
+      SBO_CUDA(cudaMemsetAsync(ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
+      k_union_count<<<(unsigned)cdiv(nw, 256), 256, 0, ctx->stream>>>(1, (const uint32_t*)ctx->m_und.p, nw, ctr + 1);
+      SBO_LAUNCH_CHECK();
+      SBO_CUDA(cudaMemcpyAsync(&h_und, ctr + 1, sizeof(h_und), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ev_end(ctx);
   }
   if (counts_host) {
     if (fantasy) SBO_CUDA(cudaMemcpyAsync(counts_host, ctx->counts.p, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1435,6 +1477,8 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
   ev_collect(ctx);
   out->n_hit = (int64_t)h[1];
   out->n_ambiguous = ps.n_ambiguous; out->n_refined_safe = ps.n_refined_safe;
+  out->n_undecided = bounds ? (int64_t)h_und : 0;
+  out->undecided_best_idx = -1; out->undecided_best_value = -INFINITY;
   if (ps.counted) out->pairs_evaluated = (int64_t)h[0] * ps.count_scale;
   else out->pairs_evaluated = ps.pairs_evaluated;
   if (out->pairs_evaluated > out->pairs_algorithmic) out->pairs_evaluated = out->pairs_algorithmic;
@@ -1451,6 +1495,10 @@ int pairs_finish(sbo_ctx* ctx, int goose, long long offset, const void* result_d
       const bool better = out->best_idx < 0 || (goose ? (val < out->best_value) : (val > out->best_value));
       if (better) { out->best_idx = idx; out->best_value = val; }
     }
+  }
+  if (bounds && out->n_undecided > 0) {
+    SBO_TRY(argreduce_run(ctx, SBO_ARGMAX_VAR0, (const uint32_t*)ctx->m_und.p, nullptr, &out->undecided_best_idx, &out->undecided_best_value));
+    acc5 += ctx->phase_ms[5];
   }
   ctx->phase_ms[5] = keep5 + acc5;
   return SBO_OK;

@@ -42,6 +42,7 @@ class GridEngine:
         self.count = 0
         self.grid_kind = None
         self.comm_ready = False
+        self.options = {}                   # what set_option was called with
         self.stream = None                  # the raw cudaStream_t the context launches on (None = its own stream)
         if stream is not None:
             self._ck(self._lib.sbo_set_stream(self._h, C.c_void_p(int(stream))))
@@ -75,6 +76,7 @@ class GridEngine:
 
     def set_option(self, name, value):
         self._ck(self._lib.sbo_set_option(self._h, name.encode(), int(value)))
+        self.options[name] = int(value)
 
     def release(self, what=3):
         """Free device workspaces: 1 = per-point V rows, 2 = gathered pair operands, 3 = both (large grids)."""
@@ -277,7 +279,8 @@ class GridEngine:
                 "per_idx": [r.per_idx[c] for c in range(nc)], "per_value": [r.per_value[c] for c in range(nc)],
                 "n_x": r.n_x, "n_z": r.n_z, "pairs_algorithmic": r.pairs_algorithmic,
                 "pairs_evaluated": r.pairs_evaluated, "n_hit": r.n_hit, "n_ambiguous": r.n_ambiguous,
-                "n_refined_safe": r.n_refined_safe}
+                "n_refined_safe": r.n_refined_safe, "n_undecided": r.n_undecided,
+                "undecided_best_idx": r.undecided_best_idx, "undecided_best_value": r.undecided_best_value}
 
     def expander(self, beta, L=None, mode=capi.MODE_LIPSCHITZ, precision=capi.PREC_FP64, want_counts=False):
         r = capi.PairResult()

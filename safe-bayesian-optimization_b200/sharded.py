@@ -168,6 +168,9 @@ def _pairs(eng, mode, prec, beta, L, goose, device, group, want_counts=False):
     n_all = gather_scalars([nx], device, group)[:, 0].astype(np.int64)
     n_total, offset = int(n_all.sum()), int(n_all[:rank].sum())
     fantasy = mode == capi.MODE_FANTASY
+    if fantasy and world > 1 and getattr(eng, "options", {}).get("fantasy_refine") == 3:
+        raise ValueError("fantasy_refine = 3 (bounds mode) on several ranks needs the library communicator: "
+                         "init_comm() / orchestrator='library' (the per-candidate undecided counts are combined there)")
     if not fantasy and world > 1 and hasattr(eng, "pairs_set_segments"):
         # reference-exact mode: the library restores grid order of the gathered candidates (compact tiles for the exact
         # culling), and the SafeOpt expander is split by CANDIDATES: all-gather of the unsafe bitmask (north_star's

@@ -43,6 +43,28 @@ def test_two_gpus_agree_with_one(mode, precision, orchestrator):
             assert b["pairs_evaluated"] <= 1.1 * a["pairs_evaluated"] + 4 * 256 * 256 * 3
 
 
+def test_bounds_mode_on_two_gpus_brackets_the_exact_set():
+    """fantasy_refine = 3: the settled counts AND the per-candidate undecided-pair counts are all-reduced inside the library.
+    The error-bound constants are maxima over the LOCAL unsafe points, so the band (and with it the certified / undecided
+    split) may move by a few pairs with the sharding -- what must hold on any sharding is the bracket around the exact set."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    common = ["--workload", "c4s", "--mode", "fantasy", "--precision", "tf32", "--steps", "1", "--warmup", "1",
+              "--no-cpu-baseline", "--no-peaks", "--no-reference-configs", "--no-lipschitz-steps"]
+    exact = _run([sys.executable, "bench.py", "--refine", "2"] + common)["config"]
+    one = _run([sys.executable, "bench.py", "--refine", "3"] + common)["config"]
+    two = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                "--master-port", "29534", "bench.py", "--gpus", "2", "--orchestrator", "library", "--refine", "3"] + common)["config"]
+    for b in (one, two):
+        for k in ["n_safe", "n_unsafe", "pairs"]:
+            assert exact[k] == b[k], k
+        assert b["refined_safe"] == 0
+        assert b["n_hit"] <= exact["n_hit"] <= b["n_hit"] + b["n_undecided"]
+        assert abs(b["refined_pairs_fp64"] - exact["refined_pairs_fp64"]) <= 0.01 * exact["refined_pairs_fp64"] + 8
+    assert abs(one["n_hit"] - two["n_hit"]) <= 0.01 * one["n_hit"] + 8
+
+
 def test_two_contexts_on_two_devices_in_one_process(oracle):
     """the >48 KB dynamic shared-memory opt-in is per device.  One process, one context per GPU: the DMMA posterior
     (112 KB) and the tcgen05 fantasy GEMM must launch on both and agree."""

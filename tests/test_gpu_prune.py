@@ -91,3 +91,45 @@ def test_refinement_list_overflow_reruns_with_an_exact_size(engine, oracle):
     assert res["tf32"]["n_ambiguous"] > 16, "the case must overflow a 16-entry list to test anything"
     assert np.abs(res["tf32"]["counts"].astype(np.int64) - res["fp64"]["counts"]).sum() <= 1
     assert res["tf32"]["best_idx"] == res["fp64"]["best_idx"]
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3"])
+def test_bounds_mode_brackets_the_fp64_expander_set(engine, precision):
+    """fantasy_refine = 3 (bounds mode, for shards whose ambiguous pairs do not fit a list): no FP64 pass; the counts are the
+    pairs the error bound SETTLES as newly safe, candidates with none of those but some pair inside the bound are reported
+    as undecided (count -1).  Against the FP64 kernel: settled counts never exceed the FP64 counts, every certified member
+    is an FP64 member, every FP64 member is certified or undecided, and x_new is the FP64 one whenever the best undecided
+    candidate cannot beat it."""
+    from sbo_b200 import _capi as capi, workloads
+    for (d, ppd, n, G, rule) in [(4, 9, 200, 4, capi.UNSAFE_ANY), (3, 14, 70, 3, capi.UNSAFE_ALL), (6, 5, 130, 3, capi.UNSAFE_ANY)]:
+        ds, lo, hi, pts, beta = workloads.small(d=d, pts_per_dim=ppd, n=n, seed=20 + d, G=G)
+        engine.set_model(ds)
+        engine.set_grid(lo, hi, pts)
+        engine.posterior(keep_v=capi.PRECISIONS["fp64"][1], fetch=False)
+        engine.sets(beta, rule)
+        exact = engine.expander(beta, None, capi.MODE_FANTASY, capi.PREC_FP64, want_counts=True)
+        prec, keep_v = capi.PRECISIONS[precision]
+        engine.posterior(keep_v=keep_v, fetch=False)
+        engine.sets(beta, rule)
+        try:
+            engine.set_option("fantasy_refine", 3)
+            lo_b = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+            engine.set_option("fantasy_refine", 2)
+            ref = engine.expander(beta, None, capi.MODE_FANTASY, prec, want_counts=True)
+        finally:
+            engine.set_option("fantasy_refine", 2)
+        assert np.array_equal(ref["counts"], exact["counts"])
+        c, e = lo_b["counts"], exact["counts"]
+        und = c < 0
+        assert np.all(c[~und] <= e[~und])
+        assert np.all(e[c > 0] > 0)                                 # certified members are FP64 members
+        assert np.all((c > 0) | und | (e == 0))                     # FP64 members are certified or undecided
+        assert lo_b["n_hit"] == int((c > 0).sum()) and lo_b["n_undecided"] == int(und.sum())
+        assert lo_b["n_hit"] <= exact["n_hit"] <= lo_b["n_hit"] + lo_b["n_undecided"]
+        assert lo_b["n_ambiguous"] == ref["n_ambiguous"] and lo_b["n_refined_safe"] == 0
+        if lo_b["n_undecided"] == 0 or lo_b["undecided_best_value"] < lo_b["best_value"]:
+            assert lo_b["best_idx"] == exact["best_idx"]
+        if lo_b["n_undecided"]:
+            assert und[lo_b["undecided_best_idx"]]
+        print(f"bounds {precision} d={d}: certified {lo_b['n_hit']}, undecided {lo_b['n_undecided']}, fp64 {exact['n_hit']}, "
+              f"ambiguous pairs {lo_b['n_ambiguous']}")
