@@ -44,3 +44,36 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "gp_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_header_is_plain_c_and_the_ctypes_structs_mirror_it(tmp_path):
+    """include/sbo_b200.h compiles as C99 (no C++ / torch types on the boundary), and the ctypes mirrors of its result
+    structs have the header's size and field offsets -- a field added on one side only would silently shift every later
+    field the binding reads."""
+    import subprocess
+    from sbo_b200 import _capi
+    mirrors = {"sbo_sets_result": _capi.SetsResult, "sbo_pair_result": _capi.PairResult,
+               "sbo_step_result": _capi.StepResult, "sbo_pairs_info": _capi.PairsInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sbo_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append(f'  printf("SBO_MAX_G %d\\n", SBO_MAX_G);')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        parts = ln.split()
+        got[tuple(parts[:-1])] = int(parts[-1])
+    assert got[("SBO_MAX_G",)] == _capi.MAX_G
+    for cname, cls in mirrors.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
